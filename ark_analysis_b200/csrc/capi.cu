@@ -1,0 +1,476 @@
+// capi.cu -- the extern "C" surface declared in include/pixie_b200.h.
+#include <float.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <mutex>
+#include <vector>
+
+#include "common.cuh"
+
+using namespace pixie;
+
+namespace {
+
+#define PX_CUDA(call)                          \
+    do {                                       \
+        cudaError_t e__ = (call);              \
+        if (e__ != cudaSuccess) {              \
+            set_last_cuda_error(e__, #call);   \
+            return PIXIE_ERR_CUDA;             \
+        }                                      \
+    } while (0)
+
+thread_local char g_last_error[512] = "";
+
+void set_last_cuda_error(cudaError_t e, const char *what)
+{
+    snprintf(g_last_error, sizeof(g_last_error), "%s: %s", what, cudaGetErrorString(e));
+}
+
+inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+__global__ void set_u64_kernel(unsigned long long *dst, unsigned long long v) { *dst = v; }
+
+// ---- cuTensorMapEncodeTiled through the runtime's driver entry point (no -lcuda link)
+typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *,
+                                  const cuuint64_t *, const cuuint64_t *, const cuuint32_t *,
+                                  const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn get_encode_fn()
+{
+    static EncodeTiledFn fn = nullptr;
+    static std::once_flag once;
+    std::call_once(once, [] {
+        void *p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) ==
+                cudaSuccess &&
+            q == cudaDriverEntryPointSuccess)
+            fn = reinterpret_cast<EncodeTiledFn>(p);
+    });
+    return fn;
+}
+
+// X [n x C] fp32, row pitch ldX: box = 32 channels x 128 rows, SWIZZLE_128B, OOB reads as zero.
+bool make_x_tensor_map(CUtensorMap *tm, const float *X, int64_t n, int C, int64_t ldX)
+{
+    EncodeTiledFn fn = get_encode_fn();
+    if (!fn) return false;
+    cuuint64_t gdim[2] = {(cuuint64_t)C, (cuuint64_t)n};
+    cuuint64_t gstride[1] = {(cuuint64_t)ldX * sizeof(float)};
+    cuuint32_t box[2] = {32u, (cuuint32_t)kTile};
+    cuuint32_t estr[2] = {1u, 1u};
+    CUresult r = fn(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float *>(X), gdim, gstride,
+                    box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                    CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) {
+        snprintf(g_last_error, sizeof(g_last_error), "cuTensorMapEncodeTiled failed: %d", (int)r);
+        return false;
+    }
+    return true;
+}
+
+int num_sms_current_device()
+{
+    static int cached[64];
+    static bool have[64];
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return 148;
+    if (!have[dev]) {
+        int v = 148;
+        cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev);
+        cached[dev] = v;
+        have[dev] = true;
+    }
+    return cached[dev];
+}
+
+// ---- workspace carve-up
+struct Workspace {
+    float *wimg;
+    CodebookAux *aux;
+    int *fixup_count;
+    float *partials;
+    int32_t *labels_scratch;
+    size_t total;
+};
+
+Workspace carve(void *base, int64_t n_visit, int C, int K)
+{
+    Workspace w{};
+    size_t off = 0;
+    const size_t wimg_max = (size_t)5 * 512 * 128;  // nblkW <= 5, Ntot <= 512
+    w.wimg = reinterpret_cast<float *>((char *)base + off);
+    off += align_up(wimg_max, 1024);
+    w.aux = reinterpret_cast<CodebookAux *>((char *)base + off);
+    off += 256;
+    w.fixup_count = reinterpret_cast<int *>((char *)base + off);
+    off += 256;
+    w.partials = reinterpret_cast<float *>((char *)base + off);
+    off += align_up((size_t)kSumParts * K * (C + 1) * sizeof(float), 256);
+    w.labels_scratch = reinterpret_cast<int32_t *>((char *)base + off);
+    const int64_t tiles = (n_visit + kTile - 1) / kTile + 1;
+    off += align_up((size_t)tiles * kTile * sizeof(int32_t), 256);
+    w.total = off;
+    return w;
+}
+
+// BMU over the tiles {tile_first + j * tile_stride}, j < ntiles.
+int bmu_tiles(const float *X, int64_t n, int C, int64_t ldX, const float *W, int K,
+              int32_t *labels, int compact, int64_t tile_first, int64_t tile_stride,
+              int64_t ntiles, const Workspace &ws, uint32_t flags, unsigned long long *stats,
+              cudaStream_t stream)
+{
+    if (ntiles <= 0) return PIXIE_OK;
+    TcPlan plan = make_tc_plan(C, K);
+    const bool aligned = ((reinterpret_cast<uintptr_t>(X) & 15u) == 0) && (ldX % 4 == 0) &&
+                         ldX >= C && n < ((int64_t)1 << 31) - kTile;
+    bool use_tc = plan.ok && aligned && !(flags & PIXIE_FLAG_FORCE_EXACT);
+    CUtensorMap tm;
+    if (use_tc && !make_x_tensor_map(&tm, X, n, C, ldX)) use_tc = false;
+    if (!use_tc) {
+        if (flags & PIXIE_FLAG_FORCE_TC) return PIXIE_ERR_UNSUPPORTED;
+        PX_CUDA(launch_bmu_exact(X, n, C, ldX, W, K, labels, tile_first, tile_stride, ntiles,
+                                 compact, nullptr, stream));
+        if (stats) {
+            set_u64_kernel<<<1, 1, 0, stream>>>(stats + PIXIE_STAT_KERNEL, 2ull);
+        }
+        return PIXIE_OK;
+    }
+    PX_CUDA(cudaMemsetAsync(ws.fixup_count, 0, sizeof(int), stream));
+    PX_CUDA(launch_codebook_prep(W, K, C, plan, ws.wimg, ws.aux, stream));
+    TcParams p{};
+    p.n = n;
+    p.tile_first = tile_first;
+    p.tile_stride = tile_stride;
+    p.ntiles = ntiles;
+    p.wimg = ws.wimg;
+    p.aux = ws.aux;
+    p.labels = labels;
+    p.compact_labels = compact;
+    p.stats = stats;
+    p.fixup_count = ws.fixup_count;
+    p.plan = plan;
+    PX_CUDA(launch_bmu_tc(tm, p, num_sms_current_device(), stream));
+    // rows the tensor-core kernel could not settle (NaN/Inf rows, degenerate codebooks): exact
+    // kernel; returns immediately when the counter is zero.
+    PX_CUDA(launch_bmu_exact(X, n, C, ldX, W, K, labels, tile_first, tile_stride, ntiles, compact,
+                             ws.fixup_count, stream));
+    if (stats) {
+        set_u64_kernel<<<1, 1, 0, stream>>>(stats + PIXIE_STAT_KERNEL, 1ull);
+    }
+    return PIXIE_OK;
+}
+
+bool bad_shape(int64_t n, int C, int64_t ldX, int K)
+{
+    return n < 0 || C < 1 || K < 1 || ldX < C || C > 4096 || K > 65535;
+}
+
+}  // namespace
+
+extern "C" {
+
+int pixie_version(void) { return 100; }
+
+const char *pixie_error_string(int code)
+{
+    switch (code) {
+        case PIXIE_OK: return "ok";
+        case PIXIE_ERR_INVALID_ARG: return "invalid argument";
+        case PIXIE_ERR_WORKSPACE: return "workspace too small";
+        case PIXIE_ERR_CUDA: return g_last_error[0] ? g_last_error : "CUDA error";
+        case PIXIE_ERR_UNSUPPORTED: return "shape not supported by the tensor-core kernel";
+        case PIXIE_ERR_NO_DEVICE: return "no CUDA device";
+        default: return "unknown error";
+    }
+}
+
+int pixie_device_count(void)
+{
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) return PIXIE_ERR_NO_DEVICE;
+    return n;
+}
+
+size_t pixie_workspace_bytes(int64_t n, int32_t C, int32_t K)
+{
+    if (n < 0 || C < 1 || K < 1) return 0;
+    return carve(nullptr, n, C, K).total;
+}
+
+int pixie_bmu_f32(const float *X, int64_t n, int32_t C, int64_t ldX, const float *W, int32_t K,
+                  int32_t *labels, double *SN_or_null, void *workspace, size_t ws_bytes,
+                  uint32_t flags, unsigned long long *stats_or_null, void *stream)
+{
+    if (bad_shape(n, C, ldX, K) || !W || !labels || (n > 0 && !X)) return PIXIE_ERR_INVALID_ARG;
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    // assignment does not use the label scratch: size the check for 0 visited rows
+    Workspace ws = carve(workspace, 0, C, K);
+    if (!workspace || ws_bytes < ws.total) return PIXIE_ERR_WORKSPACE;
+    const int64_t ntiles = (n + kTile - 1) / kTile;
+    int rc = bmu_tiles(X, n, C, ldX, W, K, labels, 0, 0, 1, ntiles, ws, flags, stats_or_null, st);
+    if (rc != PIXIE_OK) return rc;
+    if (SN_or_null)
+        PX_CUDA(launch_cluster_sums(X, n, C, ldX, labels, 0, K, 0, 1, ntiles, ws.partials,
+                                    kSumParts, SN_or_null, st));
+    return PIXIE_OK;
+}
+
+int pixie_bmu_dist_f64(const float *X, int64_t n, int32_t C, int64_t ldX, const float *W, int32_t K,
+                       const int32_t *labels, double *dists, void *stream)
+{
+    if (bad_shape(n, C, ldX, K) || !W || !labels || !dists || (n > 0 && !X))
+        return PIXIE_ERR_INVALID_ARG;
+    PX_CUDA(launch_bmu_dist(X, n, C, ldX, W, K, labels, dists,
+                            reinterpret_cast<cudaStream_t>(stream)));
+    return PIXIE_OK;
+}
+
+int pixie_som_accum_f32(const float *X, int64_t n, int32_t C, int64_t ldX, const float *W32,
+                        int32_t K, int64_t tile_first, int64_t tile_stride, double *SN,
+                        void *workspace, size_t ws_bytes, uint32_t flags,
+                        unsigned long long *stats_or_null, void *stream)
+{
+    if (bad_shape(n, C, ldX, K) || !W32 || !SN || (n > 0 && !X) || tile_first < 0 ||
+        tile_stride < 1)
+        return PIXIE_ERR_INVALID_ARG;
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    const int64_t tiles_total = (n + kTile - 1) / kTile;
+    const int64_t ntiles =
+        tile_first < tiles_total ? (tiles_total - tile_first + tile_stride - 1) / tile_stride : 0;
+    Workspace ws = carve(workspace, ntiles * kTile, C, K);
+    if (!workspace || ws_bytes < ws.total) return PIXIE_ERR_WORKSPACE;
+    int rc = bmu_tiles(X, n, C, ldX, W32, K, ws.labels_scratch, 1, tile_first, tile_stride, ntiles,
+                       ws, flags, stats_or_null, st);
+    if (rc != PIXIE_OK) return rc;
+    PX_CUDA(launch_cluster_sums(X, n, C, ldX, ws.labels_scratch, 1, K, tile_first, tile_stride,
+                                ntiles, ws.partials, kSumParts, SN, st));
+    return PIXIE_OK;
+}
+
+int pixie_som_apply_f64(double *W64, float *W32, const double *SN, int32_t xdim, int32_t ydim,
+                        int32_t C, double sigma, double alpha, void *stream)
+{
+    if (!W64 || !W32 || !SN || xdim < 1 || ydim < 1 || C < 1 || !(sigma > 0.0))
+        return PIXIE_ERR_INVALID_ARG;
+    PX_CUDA(launch_som_apply(W64, W32, SN, xdim, ydim, C, sigma, alpha,
+                             reinterpret_cast<cudaStream_t>(stream)));
+    return PIXIE_OK;
+}
+
+int pixie_som_train_f32(const float *X, int64_t n, int32_t C, int64_t ldX, double *W64, float *W32,
+                        double *SN, int32_t xdim, int32_t ydim, int32_t rlen,
+                        int32_t batches_per_pass, double alpha0, double alpha1, double radius0,
+                        double radius1, void *workspace, size_t ws_bytes, uint32_t flags,
+                        void *stream)
+{
+    if (xdim < 1 || ydim < 1 || rlen < 1 || batches_per_pass < 1 || !W64 || !W32 || !SN)
+        return PIXIE_ERR_INVALID_ARG;
+    const int K = xdim * ydim;
+    if (bad_shape(n, C, ldX, K) || (n > 0 && !X)) return PIXIE_ERR_INVALID_ARG;
+    const int64_t T = (int64_t)rlen * batches_per_pass;
+    // W32 = fp32(W64) for the first step: an apply with nothing accumulated (SN = 0) only casts
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    PX_CUDA(cudaMemsetAsync(SN, 0, sizeof(double) * (size_t)K * (C + 1), st));
+    int rc = pixie_som_apply_f64(W64, W32, SN, xdim, ydim, C, 1.0, 0.0, stream);
+    if (rc != PIXIE_OK) return rc;
+    for (int64_t t = 0; t < T; ++t) {
+        const int64_t m = t % batches_per_pass;
+        rc = pixie_som_accum_f32(X, n, C, ldX, W32, K, m, batches_per_pass, SN, workspace, ws_bytes,
+                                 flags, nullptr, stream);
+        if (rc != PIXIE_OK) return rc;
+        const double frac = (double)t / (double)T;
+        const double r = radius0 - (radius0 - radius1) * frac;
+        const double r_eff = r < 1.0 ? 0.5 : r;
+        const double alpha = alpha0 - (alpha0 - alpha1) * frac;
+        rc = pixie_som_apply_f64(W64, W32, SN, xdim, ydim, C, 0.5 * r_eff, alpha, stream);
+        if (rc != PIXIE_OK) return rc;
+    }
+    return PIXIE_OK;
+}
+
+}  // extern "C"
+
+// ------------------------------------------------------------------------------------------------
+// host-buffer entry points (H2D / kernel / D2H pipelined over two streams)
+// ------------------------------------------------------------------------------------------------
+namespace {
+
+// dst[r * ld + c] = (float)src[r * C + c]  (round to nearest), r < rows, c < C
+__global__ void f64_to_f32_kernel(const double *__restrict__ src, float *__restrict__ dst,
+                                  int64_t rows, int C, int64_t ld)
+{
+    const int64_t count = rows * C;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < count;
+         i += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t r = i / C;
+        const int c = (int)(i - r * C);
+        dst[r * ld + c] = (float)src[i];
+    }
+}
+
+struct DeviceGuard {
+    int prev;
+    explicit DeviceGuard(int p) : prev(p) {}
+    ~DeviceGuard() { cudaSetDevice(prev); }
+};
+
+struct HostCtx {
+    int device = -1;
+    cudaStream_t stream[2] = {nullptr, nullptr};
+    cudaEvent_t w_ready = nullptr;
+    void *dX[2] = {nullptr, nullptr};     // fp32 chunk
+    void *dX64[2] = {nullptr, nullptr};   // fp64 staging chunk (f64 entry point only)
+    int32_t *dLab[2] = {nullptr, nullptr};
+    double *dDist[2] = {nullptr, nullptr};
+    void *dWs[2] = {nullptr, nullptr};
+    float *dW = nullptr;
+    double *dW64 = nullptr;
+    size_t capX[2] = {0, 0}, capX64[2] = {0, 0}, capRows[2] = {0, 0}, capDist[2] = {0, 0};
+    size_t capWs[2] = {0, 0}, capW = 0, capW64 = 0;
+};
+
+std::mutex g_host_mutex;
+std::vector<HostCtx> g_host_ctx;
+
+template <typename T>
+cudaError_t ensure(T **ptr, size_t *cap, size_t need)
+{
+    if (*cap >= need) return cudaSuccess;
+    if (*ptr) cudaFree(*ptr);
+    *ptr = nullptr;
+    *cap = 0;
+    cudaError_t e = cudaMalloc(reinterpret_cast<void **>(ptr), need);
+    if (e == cudaSuccess) *cap = need;
+    return e;
+}
+
+template <typename TIn>
+int map_data_host(const TIn *nodes, int32_t K, const TIn *data, int64_t n, int32_t C,
+                  int32_t *labels, double *dists, int32_t device, int64_t chunk_rows)
+{
+    if (K < 1 || C < 1 || n < 0 || !nodes || !labels || (n > 0 && !data))
+        return PIXIE_ERR_INVALID_ARG;
+    if (n == 0) return PIXIE_OK;
+    constexpr bool kIsF64 = sizeof(TIn) == 8;
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev < 1) return PIXIE_ERR_NO_DEVICE;
+    int prev = 0;
+    PX_CUDA(cudaGetDevice(&prev));
+    if (device < 0) device = prev;
+    if (device >= ndev) return PIXIE_ERR_INVALID_ARG;
+    if (chunk_rows <= 0) chunk_rows = 1 << 20;
+    if (chunk_rows > n) chunk_rows = n;
+    chunk_rows = (chunk_rows + kTile - 1) / kTile * kTile;
+
+    std::lock_guard<std::mutex> lock(g_host_mutex);
+    DeviceGuard guard(prev);
+    PX_CUDA(cudaSetDevice(device));
+    HostCtx *ctx = nullptr;
+    for (auto &c : g_host_ctx)
+        if (c.device == device) ctx = &c;
+    if (!ctx) {
+        g_host_ctx.emplace_back();
+        ctx = &g_host_ctx.back();
+        ctx->device = device;
+        for (int s = 0; s < 2; ++s)
+            PX_CUDA(cudaStreamCreateWithFlags(&ctx->stream[s], cudaStreamNonBlocking));
+        PX_CUDA(cudaEventCreateWithFlags(&ctx->w_ready, cudaEventDisableTiming));
+    }
+    const int64_t ld = (C + 3) / 4 * 4;  // device row pitch: TMA needs 16-byte multiples
+    const size_t ws_need = pixie_workspace_bytes(0, C, K);
+    for (int s = 0; s < 2; ++s) {
+        PX_CUDA(ensure(reinterpret_cast<char **>(&ctx->dX[s]), &ctx->capX[s],
+                       (size_t)chunk_rows * ld * sizeof(float)));
+        if (kIsF64)
+            PX_CUDA(ensure(reinterpret_cast<char **>(&ctx->dX64[s]), &ctx->capX64[s],
+                           (size_t)chunk_rows * C * sizeof(double)));
+        PX_CUDA(ensure(&ctx->dLab[s], &ctx->capRows[s], (size_t)chunk_rows * sizeof(int32_t)));
+        if (dists)
+            PX_CUDA(ensure(&ctx->dDist[s], &ctx->capDist[s], (size_t)chunk_rows * sizeof(double)));
+        PX_CUDA(ensure(reinterpret_cast<char **>(&ctx->dWs[s]), &ctx->capWs[s], ws_need));
+    }
+    PX_CUDA(ensure(&ctx->dW, &ctx->capW, (size_t)K * C * sizeof(float)));
+
+    // codebook -> device (fp32)
+    cudaStream_t s0 = ctx->stream[0];
+    if (kIsF64) {
+        PX_CUDA(ensure(&ctx->dW64, &ctx->capW64, (size_t)K * C * sizeof(double)));
+        PX_CUDA(cudaMemcpyAsync(ctx->dW64, nodes, (size_t)K * C * sizeof(double),
+                                cudaMemcpyHostToDevice, s0));
+        f64_to_f32_kernel<<<64, 256, 0, s0>>>(ctx->dW64, ctx->dW, (int64_t)K, C, (int64_t)C);
+    } else {
+        PX_CUDA(cudaMemcpyAsync(ctx->dW, nodes, (size_t)K * C * sizeof(float),
+                                cudaMemcpyHostToDevice, s0));
+    }
+    PX_CUDA(cudaEventRecord(ctx->w_ready, s0));
+    PX_CUDA(cudaStreamWaitEvent(ctx->stream[1], ctx->w_ready, 0));
+
+    int rc = PIXIE_OK;
+    int64_t ci = 0;
+    for (int64_t r0 = 0; r0 < n && rc == PIXIE_OK; r0 += chunk_rows, ++ci) {
+        const int s = (int)(ci & 1);
+        cudaStream_t st = ctx->stream[s];
+        const int64_t rows = (n - r0) < chunk_rows ? (n - r0) : chunk_rows;
+        float *dX = reinterpret_cast<float *>(ctx->dX[s]);
+        if (kIsF64) {
+            PX_CUDA(cudaMemcpyAsync(ctx->dX64[s], data + (size_t)r0 * C,
+                                    (size_t)rows * C * sizeof(double), cudaMemcpyHostToDevice, st));
+            f64_to_f32_kernel<<<148 * 8, 256, 0, st>>>(
+                reinterpret_cast<const double *>(ctx->dX64[s]), dX, rows, C, ld);
+        } else if (ld == C) {
+            PX_CUDA(cudaMemcpyAsync(dX, data + (size_t)r0 * C, (size_t)rows * C * sizeof(float),
+                                    cudaMemcpyHostToDevice, st));
+        } else {
+            PX_CUDA(cudaMemcpy2DAsync(dX, (size_t)ld * sizeof(float), data + (size_t)r0 * C,
+                                      (size_t)C * sizeof(float), (size_t)C * sizeof(float),
+                                      (size_t)rows, cudaMemcpyHostToDevice, st));
+        }
+        rc = pixie_bmu_f32(dX, rows, C, ld, ctx->dW, K, ctx->dLab[s], nullptr, ctx->dWs[s],
+                           ws_need, PIXIE_FLAG_AUTO, nullptr, st);
+        if (rc != PIXIE_OK) break;
+        PX_CUDA(cudaMemcpyAsync(labels + r0, ctx->dLab[s], (size_t)rows * sizeof(int32_t),
+                                cudaMemcpyDeviceToHost, st));
+        if (dists) {
+            rc = pixie_bmu_dist_f64(dX, rows, C, ld, ctx->dW, K, ctx->dLab[s], ctx->dDist[s], st);
+            if (rc != PIXIE_OK) break;
+            PX_CUDA(cudaMemcpyAsync(dists + r0, ctx->dDist[s], (size_t)rows * sizeof(double),
+                                    cudaMemcpyDeviceToHost, st));
+        }
+    }
+    cudaError_t e0 = cudaStreamSynchronize(ctx->stream[0]);
+    cudaError_t e1 = cudaStreamSynchronize(ctx->stream[1]);
+    if (rc != PIXIE_OK) return rc;
+    if (e0 != cudaSuccess) {
+        set_last_cuda_error(e0, "stream 0");
+        return PIXIE_ERR_CUDA;
+    }
+    if (e1 != cudaSuccess) {
+        set_last_cuda_error(e1, "stream 1");
+        return PIXIE_ERR_CUDA;
+    }
+    return PIXIE_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int pixie_map_data_to_nodes_host_f32(const float *nodes, int32_t K, const float *data, int64_t n,
+                                     int32_t C, int32_t *labels, double *dists_or_null,
+                                     int32_t device, int64_t chunk_rows)
+{
+    return map_data_host<float>(nodes, K, data, n, C, labels, dists_or_null, device, chunk_rows);
+}
+
+int pixie_map_data_to_nodes_host_f64(const double *nodes, int32_t K, const double *data, int64_t n,
+                                     int32_t C, int32_t *labels, double *dists_or_null,
+                                     int32_t device, int64_t chunk_rows)
+{
+    return map_data_host<double>(nodes, K, data, n, C, labels, dists_or_null, device, chunk_rows);
+}
+
+}  // extern "C"

@@ -1,0 +1,85 @@
+// common.cuh -- shared declarations of the Pixie B200 kernels (internal; the public surface is
+// include/pixie_b200.h).
+#pragma once
+#include <cuda.h>
+#include <cuda_runtime.h>
+#include <stddef.h>
+#include <stdint.h>
+
+#include "../../include/pixie_b200.h"
+
+namespace pixie {
+
+constexpr int kTile = PIXIE_TILE;  // rows per tile == UMMA M == TMEM lanes
+constexpr int kLabelFixup = -1;    // sentinel: row must be resolved by the exact fix-up kernel
+constexpr int kMaxCand = 16;       // candidate nodes kept per row before giving up to the fix-up
+constexpr int kPairCap = 1024;     // (row, node) pairs re-evaluated per tile and epilogue group
+constexpr int kMaxStages = 6;
+
+// Device-side result of the codebook preparation kernel, read by the BMU kernel.
+struct CodebookAux {
+    float wmax;   // max_k ||w_k||   (inflated by a few ulp)
+    float wmax2;  // wmax^2
+    int nonfinite;
+    int pad;
+};
+
+// Host-side plan of the tensor-core BMU kernel for one (C, K).
+struct TcPlan {
+    bool ok;
+    int C, K;
+    int C8;      // C rounded up to the tf32 MMA K-step (8)
+    int ksteps;  // C8 / 8 data K-steps (+1 bias K-step)
+    int nblkX;   // 32-channel (128-byte) blocks of one X tile  = ceil(C / 32)
+    int nblkW;   // 32-column blocks of the codebook image      = ceil((C8 + 8) / 32)
+    int SL;      // TMEM columns per epilogue slice (template parameter of the kernel)
+    int spc;     // slices per accumulator chunk
+    int NCH;     // accumulator chunks per tile (1 or 2)
+    int Nmma;    // UMMA N = SL * spc (multiple of 16, <= 256)
+    int Ntot;    // NCH * Nmma >= K: codebook rows in the image (padded rows never win)
+    int nbuf;    // TMEM accumulator buffers (2)
+    int tmem_cols;
+    int nstage;  // X tile pipeline depth
+    uint32_t stage_bytes, wimg_bytes;
+    uint32_t off_ones, off_x, off_bar, off_cand, off_pairs, off_d2;
+    uint32_t smem_bytes;  // dynamic shared memory to request (includes 1 KiB alignment slack)
+};
+
+TcPlan make_tc_plan(int C, int K);
+
+struct TcParams {
+    int64_t n;             // rows of X
+    int64_t tile_first;    // first tile visited
+    int64_t tile_stride;   // distance between visited tiles
+    int64_t ntiles;        // number of tiles visited by this launch
+    const float *wimg;     // prepared codebook image (global)
+    const CodebookAux *aux;
+    int32_t *labels;       // labels[row] (assign) or labels[j * 128 + r] (compact, accum)
+    int compact_labels;
+    unsigned long long *stats;  // may be null
+    int *fixup_count;           // device counter of sentinel rows
+    TcPlan plan;
+};
+
+// launchers (each enqueues on `stream` and returns the cudaError_t of the launch)
+cudaError_t launch_codebook_prep(const float *W, int K, int C, const TcPlan &plan, float *wimg,
+                                 CodebookAux *aux, cudaStream_t stream);
+cudaError_t launch_bmu_tc(const CUtensorMap &tmX, const TcParams &p, int num_sms,
+                          cudaStream_t stream);
+cudaError_t launch_bmu_exact(const float *X, int64_t n, int C, int64_t ldX, const float *W, int K,
+                             int32_t *labels, int64_t tile_first, int64_t tile_stride,
+                             int64_t ntiles, int compact_labels, const int *fixup_count_or_null,
+                             cudaStream_t stream);
+cudaError_t launch_bmu_dist(const float *X, int64_t n, int C, int64_t ldX, const float *W, int K,
+                            const int32_t *labels, double *dists, cudaStream_t stream);
+cudaError_t launch_cluster_sums(const float *X, int64_t n, int C, int64_t ldX,
+                                const int32_t *labels, int compact_labels, int K,
+                                int64_t tile_first, int64_t tile_stride, int64_t ntiles,
+                                float *partials, int nparts, double *SN, cudaStream_t stream);
+cudaError_t launch_som_apply(double *W64, float *W32, const double *SN, int xdim, int ydim, int C,
+                             double sigma, double alpha, cudaStream_t stream);
+
+// number of per-CTA partial buffers the cluster-sums kernel uses
+constexpr int kSumParts = 148;
+
+}  // namespace pixie

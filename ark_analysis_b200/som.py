@@ -1,0 +1,317 @@
+"""Device-level SOM operators of the Pixie hot path, on torch CUDA tensors, plus the
+pyFlowSOM-shaped function API (``som``, ``map_data_to_nodes``) the reference binds at
+``/root/reference/src/ark/phenotyping/cluster_helpers.py:14`` and calls at ``:106-109`` / ``:152-157``.
+
+torch is plumbing here (device memory, streams, NCCL); every kernel is in libpixie_b200.so and is
+reached through the C ABI of ``include/pixie_b200.h``.  There is no CPU fallback: without a CUDA
+device or without the built library these functions raise.
+"""
+import ctypes
+
+import numpy as np
+import torch
+
+from . import _native
+from ._native import (FLAG_AUTO, FLAG_FORCE_EXACT, FLAG_FORCE_TC, NSTATS, TILE,  # noqa: F401
+                      PixieError)
+
+__all__ = [
+    "to_device_matrix", "bmu", "bmu_dists", "cluster_sums", "som_accum", "som_apply", "train_som",
+    "som", "map_data_to_nodes", "default_radius", "init_codebook_indices", "default_batches",
+    "grid_chebyshev",
+]
+
+
+# ------------------------------------------------------------------------------------------------
+# host-side pieces of the algorithm definition
+# ------------------------------------------------------------------------------------------------
+def grid_chebyshev(xdim, ydim):
+    """K x K Chebyshev distance between SOM grid nodes, node k <-> (k // ydim, k % ydim)."""
+    k = np.arange(xdim * ydim)
+    gx, gy = k // ydim, k % ydim
+    return np.maximum(np.abs(gx[:, None] - gx[None, :]),
+                      np.abs(gy[:, None] - gy[None, :])).astype(np.float64)
+
+
+def default_radius(xdim, ydim):
+    """Neighbourhood radius range (start, end): pyFlowSOM's default, the 0.67 quantile of the grid
+    distances down to 0 (6.0 for a 10x10 map, 11.0 for 20x20)."""
+    return float(np.quantile(grid_chebyshev(xdim, ydim), 0.67)), 0.0
+
+
+def init_codebook_indices(n, K, seed):
+    """Seeded choice of K distinct rows for the initial codebook.  Raises ValueError when n < K,
+    like ``numpy.random.choice(..., replace=False)`` does inside the reference dependency."""
+    return np.random.default_rng(seed).choice(n, K, replace=False)
+
+
+def default_batches(n):
+    """Mini-batches per training pass: 32, or the number of 128-row tiles when there are fewer."""
+    ntiles = (n + TILE - 1) // TILE
+    return max(1, min(32, ntiles))
+
+
+# ------------------------------------------------------------------------------------------------
+# helpers
+# ------------------------------------------------------------------------------------------------
+def _require_cuda(t, name):
+    if not isinstance(t, torch.Tensor) or not t.is_cuda:
+        raise PixieError(f"{name} must be a CUDA tensor (no CPU fallback on this path)")
+
+
+def _ptr(t):
+    return ctypes.c_void_p(t.data_ptr()) if t is not None else None
+
+
+def _stream(device):
+    return ctypes.c_void_p(torch.cuda.current_stream(device).cuda_stream)
+
+
+def _check_x(X):
+    _require_cuda(X, "X")
+    if X.dtype != torch.float32 or X.dim() != 2:
+        raise PixieError("X must be a 2-D float32 tensor")
+    if X.shape[0] > 1 and X.shape[1] > 1 and X.stride(1) != 1:
+        raise PixieError("X rows must be contiguous (stride(1) == 1)")
+    n, C = X.shape
+    ld = X.stride(0) if n > 1 else max(C, X.stride(0))
+    return n, C, ld
+
+
+def _check_w(W, C):
+    _require_cuda(W, "W")
+    if W.dtype != torch.float32 or W.dim() != 2 or W.shape[1] != C or not W.is_contiguous():
+        raise PixieError("W must be a contiguous [K, C] float32 tensor")
+    return W.shape[0]
+
+
+_ws_cache = {}
+
+
+def _workspace(n_visit, C, K, device):
+    """Per (device, stream) cached workspace, grown on demand."""
+    need = _native.lib().pixie_workspace_bytes(int(n_visit), int(C), int(K))
+    key = (device.index, torch.cuda.current_stream(device).cuda_stream)
+    ws = _ws_cache.get(key)
+    if ws is None or ws.numel() < need:
+        ws = torch.empty(need, dtype=torch.uint8, device=device)
+        _ws_cache[key] = ws
+    return ws
+
+
+def to_device_matrix(data, device=None, out=None):
+    """Flatten a host [n, C] array (any float dtype) into the device layout the kernels stream:
+    fp32, row-major, row pitch rounded up to 4 floats (16 bytes, the TMA stride granule), zero
+    padded.  Returns the [n, C] view (stride(0) = pitch)."""
+    if device is None:
+        device = torch.device("cuda", torch.cuda.current_device())
+    device = torch.device(device)
+    if isinstance(data, torch.Tensor):
+        src = data
+    else:
+        src = torch.from_numpy(np.ascontiguousarray(data))
+    if src.dim() != 2:
+        raise PixieError("data must be 2-D")
+    n, C = src.shape
+    ld = (C + 3) // 4 * 4
+    if out is None:
+        out = torch.zeros((max(n, 1), ld), dtype=torch.float32, device=device)
+    view = out[:n, :C]
+    if n:
+        view.copy_(src.to(device=device, non_blocking=True))  # fp64 -> fp32 rounds to nearest
+    return view
+
+
+# ------------------------------------------------------------------------------------------------
+# operators
+# ------------------------------------------------------------------------------------------------
+def bmu(X, W, labels=None, want_sums=False, flags=FLAG_AUTO, stats=None):
+    """Best-matching-unit labels (1-indexed int32) of every row of X against codebook W.
+
+    Bit-identical to pyFlowSOM.map_data_to_nodes(W, X)[0] evaluated in fp64 on the same
+    fp32-representable inputs (cluster_helpers.py:152-157).  With ``want_sums`` also returns the
+    per-node channel sums and counts ``SN`` [K, C+1] (float64) of the assigned rows.
+    """
+    n, C, ld = _check_x(X)
+    K = _check_w(W, C)
+    dev = X.device
+    if labels is None:
+        labels = torch.empty(n, dtype=torch.int32, device=dev)
+    elif labels.dtype != torch.int32 or labels.numel() != n or not labels.is_contiguous():
+        raise PixieError("labels must be a contiguous int32 tensor of length n")
+    SN = torch.empty((K, C + 1), dtype=torch.float64, device=dev) if want_sums else None
+    if n == 0:
+        if SN is not None:
+            SN.zero_()
+        return (labels, SN) if want_sums else labels
+    with torch.cuda.device(dev):
+        ws = _workspace(0, C, K, dev)
+        rc = _native.lib().pixie_bmu_f32(_ptr(X), n, C, ld, _ptr(W), K, _ptr(labels), _ptr(SN),
+                                         _ptr(ws), ws.numel(), flags, _ptr(stats), _stream(dev))
+    _native.check(rc, "pixie_bmu_f32")
+    return (labels, SN) if want_sums else labels
+
+
+def bmu_dists(X, W, labels):
+    """Exact fp64 distance of each row to its assigned node (map_data_to_nodes()[1])."""
+    n, C, ld = _check_x(X)
+    K = _check_w(W, C)
+    dists = torch.empty(n, dtype=torch.float64, device=X.device)
+    if n:
+        with torch.cuda.device(X.device):
+            rc = _native.lib().pixie_bmu_dist_f64(_ptr(X), n, C, ld, _ptr(W), K, _ptr(labels),
+                                                  _ptr(dists), _stream(X.device))
+        _native.check(rc, "pixie_bmu_dist_f64")
+    return dists
+
+
+def cluster_sums(X, W, labels=None):
+    """(labels, SN): labels plus per-node channel sums / counts -- one fused call."""
+    return bmu(X, W, labels=labels, want_sums=True)
+
+
+def som_accum(X, W32, tile_first, tile_stride, SN=None, flags=FLAG_AUTO, stats=None):
+    """One mini-batch of the batch SOM: BMU of the rows of tiles tile_first, tile_first+stride, ...
+    against W32 and their per-node sums/counts SN [K, C+1] float64."""
+    n, C, ld = _check_x(X)
+    K = _check_w(W32, C)
+    dev = X.device
+    if SN is None:
+        SN = torch.empty((K, C + 1), dtype=torch.float64, device=dev)
+    ntiles = (n + TILE - 1) // TILE
+    nvis = max(0, (ntiles - tile_first + tile_stride - 1) // tile_stride) * TILE
+    with torch.cuda.device(dev):
+        ws = _workspace(nvis, C, K, dev)
+        rc = _native.lib().pixie_som_accum_f32(_ptr(X), n, C, ld, _ptr(W32), K, int(tile_first),
+                                               int(tile_stride), _ptr(SN), _ptr(ws), ws.numel(),
+                                               flags, _ptr(stats), _stream(dev))
+    _native.check(rc, "pixie_som_accum_f32")
+    return SN
+
+
+def som_apply(W64, W32, SN, xdim, ydim, sigma, alpha):
+    """Batch update of the fp64 master codebook from SN; refreshes the fp32 copy in place."""
+    K, C = W64.shape
+    with torch.cuda.device(W64.device):
+        rc = _native.lib().pixie_som_apply_f64(_ptr(W64), _ptr(W32), _ptr(SN), xdim, ydim, C,
+                                               float(sigma), float(alpha), _stream(W64.device))
+    _native.check(rc, "pixie_som_apply_f64")
+
+
+def step_schedule(t, T, alpha_range, radius_range):
+    """(sigma, alpha) of step t of T."""
+    frac = t / T
+    r = radius_range[0] - (radius_range[0] - radius_range[1]) * frac
+    r_eff = 0.5 if r < 1.0 else r
+    alpha = alpha_range[0] - (alpha_range[0] - alpha_range[1]) * frac
+    return 0.5 * r_eff, alpha
+
+
+def train_som(X, W0, xdim, ydim, rlen=1, alpha_range=(0.05, 0.01), radius_range=None,
+              batches_per_pass=None, flags=FLAG_AUTO, group=None, tile_offset=0):
+    """Batch SOM on a device-resident fp32 matrix.  ``W0`` [K, C] is the initial codebook (any
+    float dtype, host or device).  Returns the trained codebook as a float64 CUDA tensor.
+
+    Single GPU (``group is None``): one C call enqueues all rlen * B steps back to back.
+    Multi GPU: X is this rank's row shard whose first row is global tile ``tile_offset``; every step
+    all-reduces the K x (C+1) statistics over ``group`` (NCCL) between accumulate and apply, so all
+    ranks hold the same codebook.
+    """
+    n, C, ld = _check_x(X)
+    dev = X.device
+    K = xdim * ydim
+    if radius_range is None:
+        radius_range = default_radius(xdim, ydim)
+    W64 = torch.as_tensor(np.asarray(W0) if not isinstance(W0, torch.Tensor) else W0)
+    W64 = W64.to(device=dev, dtype=torch.float64).contiguous().clone()
+    if tuple(W64.shape) != (K, C):
+        raise PixieError("initial codebook must be [xdim*ydim, C]")
+    W32 = torch.empty((K, C), dtype=torch.float32, device=dev)
+    SN = torch.zeros((K, C + 1), dtype=torch.float64, device=dev)
+    distributed = group is not None
+    if batches_per_pass is None:
+        if distributed:
+            raise PixieError("batches_per_pass must be given explicitly in a multi-GPU run")
+        batches_per_pass = default_batches(n)
+    B = int(batches_per_pass)
+    if not distributed:
+        with torch.cuda.device(dev):
+            ntiles = (n + TILE - 1) // TILE
+            ws = _workspace(((ntiles + B - 1) // B + 1) * TILE, C, K, dev)
+            rc = _native.lib().pixie_som_train_f32(
+                _ptr(X), n, C, ld, _ptr(W64), _ptr(W32), _ptr(SN), xdim, ydim, int(rlen), B,
+                float(alpha_range[0]), float(alpha_range[1]), float(radius_range[0]),
+                float(radius_range[1]), _ptr(ws), ws.numel(), flags, _stream(dev))
+        _native.check(rc, "pixie_som_train_f32")
+        return W64
+    import torch.distributed as dist
+    T = int(rlen) * B
+    som_apply(W64, W32, SN, xdim, ydim, 1.0, 0.0)  # W32 = fp32(W64)
+    for t in range(T):
+        m = t % B
+        first = (m - tile_offset) % B  # local tiles whose GLOBAL index is congruent to m mod B
+        som_accum(X, W32, first, B, SN=SN, flags=flags)
+        dist.all_reduce(SN, op=dist.ReduceOp.SUM, group=group)
+        sigma, alpha = step_schedule(t, T, alpha_range, radius_range)
+        som_apply(W64, W32, SN, xdim, ydim, sigma, alpha)
+    return W64
+
+
+# ------------------------------------------------------------------------------------------------
+# pyFlowSOM-shaped function API (the numeric plugin boundary)
+# ------------------------------------------------------------------------------------------------
+def _default_device():
+    if not torch.cuda.is_available():
+        raise PixieError("no CUDA device: the Pixie SOM path has no CPU fallback")
+    return torch.device("cuda", torch.cuda.current_device())
+
+
+def som(data, xdim=10, ydim=10, rlen=10, alpha_range=(0.05, 0.01), radius_range=None, seed=None,
+        batches_per_pass=None, device=None):
+    """Drop-in for ``pyFlowSOM.som`` as ark calls it (cluster_helpers.py:106-109): trains an
+    xdim x ydim SOM on ``data`` [n, C] and returns the codebook as a float64 ndarray [K, C].
+
+    Trains the batch SOM of DESIGN.md section 4 (not pyFlowSOM's sequential online rule)."""
+    device = torch.device(device) if device is not None else _default_device()
+    data = np.asarray(data)
+    if data.ndim != 2:
+        raise ValueError("data must be a 2-D array")
+    n, C = data.shape
+    K = xdim * ydim
+    idx = init_codebook_indices(n, K, seed)
+    X = to_device_matrix(data, device)
+    # the initial codebook is taken from the fp32 device matrix so that a caller holding only the
+    # device matrix gets the same result
+    W0 = X[torch.as_tensor(idx, device=device)].to(torch.float64)
+    W = train_som(X, W0, xdim, ydim, rlen=rlen, alpha_range=alpha_range,
+                  radius_range=radius_range, batches_per_pass=batches_per_pass)
+    return W.cpu().numpy()
+
+
+def map_data_to_nodes(nodes, newdata, device=None, chunk_rows=1 << 20):
+    """Drop-in for ``pyFlowSOM.map_data_to_nodes`` (cluster_helpers.py:152-157): returns
+    ``(labels int32 1-indexed, dists float64)`` for host arrays, through the host-buffer C entry
+    point (pinned-or-pageable host memory in, chunked H2D / kernel / D2H overlap)."""
+    device = torch.device(device) if device is not None else _default_device()
+    nodes = np.ascontiguousarray(nodes)
+    newdata = np.ascontiguousarray(newdata)
+    if nodes.ndim != 2 or newdata.ndim != 2 or nodes.shape[1] != newdata.shape[1]:
+        raise ValueError("nodes [K, C] and newdata [m, C] must agree on C")
+    m, C = newdata.shape
+    K = nodes.shape[0]
+    labels = np.empty(m, np.int32)
+    dists = np.empty(m, np.float64)
+    if m == 0:
+        return labels, dists
+    L = _native.lib()
+    if newdata.dtype == np.float32 and nodes.dtype == np.float32:
+        fn = L.pixie_map_data_to_nodes_host_f32
+    else:
+        nodes = nodes.astype(np.float64, copy=False)
+        newdata = newdata.astype(np.float64, copy=False)
+        fn = L.pixie_map_data_to_nodes_host_f64
+    rc = fn(nodes.ctypes.data_as(ctypes.c_void_p), K, newdata.ctypes.data_as(ctypes.c_void_p), m, C,
+            labels.ctypes.data_as(ctypes.c_void_p), dists.ctypes.data_as(ctypes.c_void_p),
+            device.index if device.index is not None else -1, int(chunk_rows))
+    _native.check(rc, "pixie_map_data_to_nodes_host")
+    return labels, dists

@@ -1,0 +1,131 @@
+/*
+ * pixie_b200.h -- C ABI of libpixie_b200.so: the B200 (sm_100a) implementation of the Pixie SOM
+ * hot path of angelolab/ark-analysis.
+ *
+ * The reference's arithmetic for this path is two functions of the third-party pyFlowSOM module,
+ * bound at src/ark/phenotyping/cluster_helpers.py:14 and called at :106-109 (`som`) and :152-157
+ * (`map_data_to_nodes`).  Every entry point below cites the reference interface it replaces.
+ *
+ * Conventions
+ *  - plain C types only; no torch / C++ types cross this boundary.
+ *  - "device" entry points take device pointers valid on the CURRENT CUDA device and a
+ *    cudaStream_t passed as void* (NULL = default stream).  They only enqueue work (asynchronous,
+ *    never synchronise, never allocate) and are re-entrant across streams provided each call is
+ *    given its own workspace.
+ *  - "host" entry points take host pointers, do their own staging and synchronise before returning.
+ *  - return value: 0 = PIXIE_OK, negative = error (pixie_error_string()).  Nothing throws.
+ *  - matrices are row-major fp32; `ld*` is the row pitch in elements.  The tensor-core path needs
+ *    X 16-byte aligned and ldX % 4 == 0; anything else is routed to the (slow, exact) fp64 kernel.
+ *  - labels are 1-indexed int32 exactly as pyFlowSOM returns them (0 = row holds NaN/Inf).
+ */
+#ifndef PIXIE_B200_H
+#define PIXIE_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define PIXIE_OK 0
+#define PIXIE_ERR_INVALID_ARG (-1)
+#define PIXIE_ERR_WORKSPACE (-2)
+#define PIXIE_ERR_CUDA (-3)
+#define PIXIE_ERR_UNSUPPORTED (-4)
+#define PIXIE_ERR_NO_DEVICE (-5)
+
+/* rows per tile: the unit in which mini-batches of the batch SOM are interleaved */
+#define PIXIE_TILE 128
+
+/* flags for pixie_bmu_f32 / pixie_som_accum_f32 */
+#define PIXIE_FLAG_AUTO 0u        /* tensor-core kernel when the shape allows, else exact kernel */
+#define PIXIE_FLAG_FORCE_EXACT 1u /* fp64 brute-force kernel (bit-exact by construction; slow) */
+#define PIXIE_FLAG_FORCE_TC 2u    /* fail with PIXIE_ERR_UNSUPPORTED instead of falling back */
+
+/* slots of the optional device-side statistics array (uint64[PIXIE_NSTATS], accumulated) */
+#define PIXIE_STAT_ROWS_FLAGGED 0  /* rows with >= 2 tensor-core candidates */
+#define PIXIE_STAT_PAIRS 1         /* (row, node) pairs re-evaluated in fp32 */
+#define PIXIE_STAT_ROWS_FP64 2     /* rows resolved by the fp64 replica of the reference loop */
+#define PIXIE_STAT_ROWS_FIXUP 3    /* rows sent to the exact fix-up kernel (NaN/Inf/overflow) */
+#define PIXIE_STAT_KERNEL 4        /* 1 = tensor-core kernel ran, 2 = exact kernel ran */
+#define PIXIE_NSTATS 8
+
+int pixie_version(void);
+const char *pixie_error_string(int code);
+/* number of CUDA devices visible, or a negative error */
+int pixie_device_count(void);
+
+/* Bytes of device workspace pixie_bmu_f32 / pixie_som_accum_f32 need for these shapes. */
+size_t pixie_workspace_bytes(int64_t n, int32_t C, int32_t K);
+
+/*
+ * BMU assignment.  Replaces pyFlowSOM.map_data_to_nodes(nodes, newdata)[0]
+ * (cluster_helpers.py:152-157): labels[i] = 1 + argmin_k sqrt(sum_j (X[i,j] - W[k,j])^2), fp64
+ * arithmetic on the fp32 inputs, first minimum wins, 0 for rows with NaN.
+ *   X [n x C] ldX, W [K x C] contiguous, labels int32[n], all device memory.
+ *   SN_or_null: optional double[K x (C+1)] -- per-node channel sums and count of the rows
+ *   assigned to it ([S_k0..S_k,C-1, n_k]); overwritten.  This is the aggregate
+ *   compute_pixel_cluster_channel_avg builds per FOV (pixel_cluster_utils.py:369-374).
+ *   stats_or_null: optional uint64[PIXIE_NSTATS], accumulated (caller zeroes it).
+ */
+int pixie_bmu_f32(const float *X, int64_t n, int32_t C, int64_t ldX, const float *W, int32_t K,
+                  int32_t *labels, double *SN_or_null, void *workspace, size_t ws_bytes,
+                  uint32_t flags, unsigned long long *stats_or_null, void *stream);
+
+/* Exact fp64 distance to the assigned node: dists[i] = sqrt(sum_j (X[i,j]-W[labels[i]-1,j])^2),
+ * DBL_MAX when labels[i] == 0.  The second array map_data_to_nodes returns. */
+int pixie_bmu_dist_f64(const float *X, int64_t n, int32_t C, int64_t ldX, const float *W, int32_t K,
+                       const int32_t *labels, double *dists, void *stream);
+
+/*
+ * One mini-batch step of the batch SOM (the B200 replacement for pyFlowSOM.som's inner loop,
+ * cluster_helpers.py:106-109; algorithm in DESIGN.md section 4).  Visits tiles
+ * tile_first, tile_first + tile_stride, ... (< ceil(n / PIXIE_TILE)), finds each row's BMU against
+ * W32 and writes SN = double[K x (C+1)] per-node sums and counts.  In a multi-GPU run the caller
+ * all-reduces SN (sum) across ranks before pixie_som_apply_f64.
+ */
+int pixie_som_accum_f32(const float *X, int64_t n, int32_t C, int64_t ldX, const float *W32,
+                        int32_t K, int64_t tile_first, int64_t tile_stride, double *SN,
+                        void *workspace, size_t ws_bytes, uint32_t flags,
+                        unsigned long long *stats_or_null, void *stream);
+
+/* Applies one batch update to the fp64 master codebook and refreshes its fp32 copy:
+ *   H[k,b] = exp(-cheb(k,b)^2 / (2 sigma^2)); num_k = sum_b H[k,b] S_b; den_k = sum_b H[k,b] n_b;
+ *   den_k > 0: W64_k += (1 - (1 - alpha)^den_k) (num_k / den_k - W64_k);  W32 = (float)W64. */
+int pixie_som_apply_f64(double *W64, float *W32, const double *SN, int32_t xdim, int32_t ydim,
+                        int32_t C, double sigma, double alpha, void *stream);
+
+/*
+ * Whole single-GPU training run: rlen passes x batches_per_pass steps of accum + apply, enqueued
+ * back to back with no host synchronisation.  W64 [K x C] holds the initial codebook on entry and
+ * the trained codebook when the stream drains; W32 [K x C] is scratch/out.  SN is double[K x (C+1)]
+ * scratch.  Replaces pyFlowSOM.som for a device-resident fp32 matrix.
+ */
+int pixie_som_train_f32(const float *X, int64_t n, int32_t C, int64_t ldX, double *W64, float *W32,
+                        double *SN, int32_t xdim, int32_t ydim, int32_t rlen,
+                        int32_t batches_per_pass, double alpha0, double alpha1, double radius0,
+                        double radius1, void *workspace, size_t ws_bytes, uint32_t flags,
+                        void *stream);
+
+/*
+ * Host-buffer entry point with pyFlowSOM.map_data_to_nodes' shape (what a ctypes/cgo/JNI binding
+ * of the reference would call): nodes [K x C] and data [n x C] in HOST memory (fp32, row-major,
+ * contiguous), labels int32[n] and optional dists double[n] in host memory.  Streams the rows
+ * through the GPU in chunks (H2D, kernel, D2H overlapped on two streams) and returns when the
+ * labels are on the host.  device < 0 = current device.
+ */
+int pixie_map_data_to_nodes_host_f32(const float *nodes, int32_t K, const float *data, int64_t n,
+                                     int32_t C, int32_t *labels, double *dists_or_null,
+                                     int32_t device, int64_t chunk_rows);
+
+/* Same boundary with the reference's fp64 arrays (cluster_helpers.py:153-156 casts to float64):
+ * values are rounded to fp32 on the host while staging. */
+int pixie_map_data_to_nodes_host_f64(const double *nodes, int32_t K, const double *data, int64_t n,
+                                     int32_t C, int32_t *labels, double *dists_or_null,
+                                     int32_t device, int64_t chunk_rows);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PIXIE_B200_H */
