@@ -79,6 +79,9 @@ TcPlan make_tc_plan(int C, int K)
     if (p.off_x + scratch + 2u * p.stage_bytes > limit) return p;
     p.nstage = (int)((limit - p.off_x - scratch) / p.stage_bytes);
     if (p.nstage > kMaxStages) p.nstage = kMaxStages;
+    // even depth: stage (it % nstage) is then always consumed by the same epilogue group (it % 2),
+    // so no consumer can reach a full-barrier wait one phase early (parity aliasing).
+    p.nstage &= ~1;
     p.off_bar = p.off_x + (uint32_t)p.nstage * p.stage_bytes;
     p.off_cand = p.off_bar + 256u;
     p.off_pairs = p.off_cand + 256u * kMaxCand * 2u;
@@ -386,6 +389,11 @@ bmu_tc_kernel(const __grid_constant__ CUtensorMap tmX, const TcParams p)
                 const int64_t q = it * pl.NCH + c;
                 const int buf = (int)(q & 1);
                 const uint32_t bph = (uint32_t)((q >> 1) & 1);
+                // With two chunks per tile both groups alternate on the same accumulator buffer, so
+                // this group may get here a whole phase early, where a parity wait would alias and
+                // fall through.  Waiting first for the previous use's release (made by the OTHER
+                // group, after it saw the previous commit) pins the barrier to the right phase.
+                if (pl.NCH > 1 && q >= 2) mbar_wait(bar_tempty + 8u * buf, bph ^ 1u);
                 mbar_wait(bar_tfull + 8u * buf, bph);
                 tc_fence_after();
                 for (int sidx = 0; sidx < pl.spc; ++sidx) {
