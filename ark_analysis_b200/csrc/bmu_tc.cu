@@ -16,12 +16,15 @@
 //   stage 3 (CUDA cores, fp64, rare): the reference's own operation sequence (subtract, multiply,
 //           add in channel order, sqrt, strict <, lowest index first) on the survivors.
 //   Rows that defeat this (NaN/Inf, > kMaxCand candidates, pair-buffer overflow) get a sentinel
-//   label and are resolved by the exact fp64 kernel (bmu_exact.cu) launched right behind.
+//   label and are resolved by the exact fp64 kernel (som_kernels.cu) launched right behind.
 //
-// Warp roles (320 threads, 1 CTA per SM, persistent over tiles):
-//   warps 0-3 / 4-7 : two epilogue groups, alternating tiles (thread <-> tile row <-> TMEM lane)
-//   warp 8          : TMA producer (one elected lane)
-//   warp 9          : TMEM allocator + MMA issuer (one elected lane)
+// Warp roles (NG*128 + 64 threads, 1 CTA per SM, persistent over tiles):
+//   warps 0 .. 4*NG-1 : NG epilogue groups of 4 warps; group g owns tiles g, g+NG, ... of the CTA
+//                       (thread <-> tile row <-> TMEM lane; warp w reads lane quadrant w % 4)
+//   warp 4*NG         : TMA producer (one elected lane)
+//   warp 4*NG+1       : TMEM allocator + MMA issuer (one elected lane)
+// NG = 4 with 56-column slices (<= 112 registers/thread) for K <= 128, NG = 2 with wider slices
+// above that.  The epilogue is instruction-latency bound, so warps per scheduler matter.
 #include <float.h>
 
 #include "common.cuh"
@@ -34,61 +37,68 @@ using namespace ptx;
 // ------------------------------------------------------------------------------------------------
 // plan
 // ------------------------------------------------------------------------------------------------
+namespace {
+struct Variant {
+    int SL, spc, NCH, NG;
+};
+// every entry has a template instantiation in launch_bmu_tc()
+const Variant kVariants[] = {
+    {32, 1, 1, 4}, {32, 2, 1, 4}, {48, 2, 1, 4}, {56, 2, 1, 4}, {64, 2, 1, 4},
+    {32, 1, 1, 2}, {32, 2, 1, 2}, {48, 2, 1, 2}, {56, 2, 1, 2}, {64, 2, 1, 2},
+    {80, 2, 1, 2}, {104, 2, 1, 2}, {128, 2, 1, 2}, {80, 2, 2, 2}, {104, 2, 2, 2}, {128, 2, 2, 2},
+};
+}  // namespace
+
 TcPlan make_tc_plan(int C, int K)
 {
-    TcPlan p{};
-    p.ok = false;
-    p.C = C;
-    p.K = K;
-    if (C < 1 || C > 128 || K < 1 || K > 512) return p;
-    p.C8 = (C + 7) / 8 * 8;
-    p.ksteps = p.C8 / 8;
-    p.nblkX = (C + 31) / 32;
-    p.nblkW = (p.C8 + 8 + 31) / 32;
-    static const int kSL[] = {32, 64, 80, 96, 104, 112, 128};
-    long best = -1;
-    for (int SL : kSL)
-        for (int spc = 1; spc <= 8; ++spc) {
-            int Nmma = SL * spc;
-            if (Nmma > 256 || Nmma % 16) continue;
-            for (int NCH = 1; NCH <= 2; ++NCH) {
-                int Ntot = NCH * Nmma;
-                if (Ntot < K || Ntot > 512) continue;
-                long cost = (long)Ntot * 64 + NCH * spc * 8 + NCH;
-                if (best < 0 || cost < best) {
-                    best = cost;
-                    p.SL = SL;
-                    p.spc = spc;
-                    p.NCH = NCH;
-                    p.Nmma = Nmma;
-                    p.Ntot = Ntot;
-                }
-            }
+    TcPlan best{};
+    best.ok = false;
+    if (C < 1 || C > 128 || K < 1 || K > 512) return best;
+    long best_cost = -1;
+    for (const Variant &v : kVariants) {
+        TcPlan p{};
+        p.C = C;
+        p.K = K;
+        p.C8 = (C + 7) / 8 * 8;
+        p.ksteps = p.C8 / 8;
+        p.nblkX = (C + 31) / 32;
+        p.nblkW = (p.C8 + 8 + 31) / 32;
+        p.SL = v.SL;
+        p.spc = v.spc;
+        p.NCH = v.NCH;
+        p.NG = v.NG;
+        p.Nmma = v.SL * v.spc;
+        p.Ntot = p.Nmma * v.NCH;
+        if (p.Ntot < K) continue;
+        p.nbuf = v.NCH == 1 ? v.NG : 2;
+        const int need = p.nbuf * p.Nmma;
+        if (need > 512) continue;
+        p.tmem_cols = 32;
+        while (p.tmem_cols < need) p.tmem_cols *= 2;
+        p.stage_bytes = (uint32_t)p.nblkX * 16384u;
+        p.wimg_bytes = (uint32_t)p.nblkW * (uint32_t)p.Ntot * 128u;
+        p.off_ones = p.wimg_bytes;
+        p.off_x = p.off_ones + 4096u;
+        const uint32_t scratch = 256u + (uint32_t)(4 * v.NG) * kWarpPairCap * 8u;
+        const uint32_t limit = 227u * 1024u - 1024u;
+        if (p.off_x + scratch + (uint32_t)v.NG * p.stage_bytes > limit) continue;
+        p.nstage = (int)((limit - p.off_x - scratch) / p.stage_bytes);
+        if (p.nstage > kMaxStages) p.nstage = kMaxStages;
+        // a multiple of NG: stage (it % nstage) is then always consumed by the same epilogue group
+        // (it % NG), so no consumer can reach a full-barrier wait a phase early (parity aliasing).
+        p.nstage = p.nstage / v.NG * v.NG;
+        p.off_bar = p.off_x + (uint32_t)p.nstage * p.stage_bytes;
+        p.off_pairs = p.off_bar + 256u;
+        p.smem_bytes = p.off_pairs + (uint32_t)(4 * v.NG) * kWarpPairCap * 8u + 1024u;
+        p.ok = true;
+        // fewest padded codebook rows first; then more epilogue groups; then deeper pipeline
+        const long cost = (long)p.Ntot * 1000 - v.NG * 10 - p.nstage;
+        if (best_cost < 0 || cost < best_cost) {
+            best_cost = cost;
+            best = p;
         }
-    if (best < 0) return p;
-    p.nbuf = 2;
-    int need = 2 * p.Nmma;
-    p.tmem_cols = 32;
-    while (p.tmem_cols < need) p.tmem_cols *= 2;
-    p.stage_bytes = (uint32_t)p.nblkX * 16384u;
-    p.wimg_bytes = (uint32_t)p.nblkW * (uint32_t)p.Ntot * 128u;
-    p.off_ones = p.wimg_bytes;
-    p.off_x = p.off_ones + 4096u;
-    const uint32_t scratch = 256u + 256u * kMaxCand * 2u + 2u * kPairCap * 4u + 2u * kPairCap * 4u;
-    const uint32_t limit = 227u * 1024u - 1024u;
-    if (p.off_x + scratch + 2u * p.stage_bytes > limit) return p;
-    p.nstage = (int)((limit - p.off_x - scratch) / p.stage_bytes);
-    if (p.nstage > kMaxStages) p.nstage = kMaxStages;
-    // even depth: stage (it % nstage) is then always consumed by the same epilogue group (it % 2),
-    // so no consumer can reach a full-barrier wait one phase early (parity aliasing).
-    p.nstage &= ~1;
-    p.off_bar = p.off_x + (uint32_t)p.nstage * p.stage_bytes;
-    p.off_cand = p.off_bar + 256u;
-    p.off_pairs = p.off_cand + 256u * kMaxCand * 2u;
-    p.off_d2 = p.off_pairs + 2u * kPairCap * 4u;
-    p.smem_bytes = p.off_d2 + 2u * kPairCap * 4u + 1024u;
-    p.ok = true;
-    return p;
+    }
+    return best;
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -106,31 +116,32 @@ __device__ __forceinline__ uint32_t img_offset(int Ntot, int row, int col)
            (uint32_t)((((cc >> 2) ^ (row & 7)) << 4) + ((cc & 3) << 2));
 }
 
-__global__ void codebook_prep_kernel(const float *__restrict__ W, int K, int C, int C8, int nblkW,
-                                     int Ntot, float *__restrict__ wimg,
-                                     CodebookAux *__restrict__ aux)
+// one warp per codebook row; lanes stride over the image columns (coalesced reads of W)
+__global__ void __launch_bounds__(256)
+codebook_prep_kernel(const float *__restrict__ W, int K, int C, int C8, int nblkW, int Ntot,
+                     float *__restrict__ wimg, CodebookAux *__restrict__ aux)
 {
-    __shared__ float s_max[32];
-    __shared__ int s_bad;
-    if (threadIdx.x == 0) s_bad = 0;
-    __syncthreads();
+    const int lane = threadIdx.x & 31;
+    const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (row >= Ntot) return;
     const int ncols = nblkW * 32;
-    float local_max = 0.f;
-    for (int row = threadIdx.x; row < Ntot; row += blockDim.x) {
-        double nrm2 = 0.0;
-        bool bad = false;
-        for (int col = 0; col < ncols; ++col) {
-            float v = 0.f;
-            if (row < K && col < C) {
-                const float w = W[(size_t)row * C + col];
-                if (!(fabsf(w) <= FLT_MAX)) bad = true;
-                nrm2 += (double)w * (double)w;
-                v = -2.0f * w;
-            }
-            if (col < C8 || col >= C8 + 3)
-                *reinterpret_cast<float *>(reinterpret_cast<char *>(wimg) +
-                                           img_offset(Ntot, row, col)) = v;
+    char *base = reinterpret_cast<char *>(wimg);
+    double nrm2 = 0.0;
+    bool bad = false;
+    for (int col = lane; col < ncols; col += 32) {
+        float v = 0.f;
+        if (row < K && col < C) {
+            const float w = W[(size_t)row * C + col];
+            if (!(fabsf(w) <= FLT_MAX)) bad = true;
+            nrm2 += (double)w * (double)w;
+            v = -2.0f * w;
         }
+        if (col < C8 || col >= C8 + 3)
+            *reinterpret_cast<float *>(base + img_offset(Ntot, row, col)) = v;
+    }
+    for (int o = 16; o > 0; o >>= 1) nrm2 += __shfl_xor_sync(~0u, nrm2, o);
+    bad = __any_sync(~0u, bad);
+    if (lane == 0) {
         float bias = (row < K) ? (float)nrm2 : 1.0e30f;
         if (!(bias <= FLT_MAX)) bias = FLT_MAX;  // overflowed norms: row can never win anyway
         // three tf32-exact pieces (11 significant bits each): h + m + l == bias exactly
@@ -138,34 +149,25 @@ __global__ void codebook_prep_kernel(const float *__restrict__ W, int K, int C, 
         const float r1 = bias - h;
         const float m = __uint_as_float(__float_as_uint(r1) & 0xFFFFE000u);
         const float l = r1 - m;
-        char *base = reinterpret_cast<char *>(wimg);
         *reinterpret_cast<float *>(base + img_offset(Ntot, row, C8 + 0)) = h;
         *reinterpret_cast<float *>(base + img_offset(Ntot, row, C8 + 1)) = m;
         *reinterpret_cast<float *>(base + img_offset(Ntot, row, C8 + 2)) = l;
         if (row < K) {
-            if (bad) atomicOr(&s_bad, 1);
-            const float nr = (float)sqrt(nrm2);
-            if (nr <= FLT_MAX) local_max = fmaxf(local_max, nr);
+            if (bad) atomicOr(&aux->nonfinite, 1);
+            float nr = (float)sqrt(nrm2) * 1.0000005f;
+            if (!(nr <= FLT_MAX)) nr = FLT_MAX;
+            atomicMax(&aux->wmax_bits, __float_as_int(nr));  // non-negative floats order as ints
         }
-    }
-    for (int o = 16; o > 0; o >>= 1) local_max = fmaxf(local_max, __shfl_xor_sync(~0u, local_max, o));
-    if ((threadIdx.x & 31) == 0) s_max[threadIdx.x >> 5] = local_max;
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        float mx = 0.f;
-        for (int i = 0; i < (int)(blockDim.x >> 5); ++i) mx = fmaxf(mx, s_max[i]);
-        mx *= 1.0000005f;
-        aux->wmax = mx;
-        aux->wmax2 = mx * mx;
-        aux->nonfinite = s_bad;
-        aux->pad = 0;
     }
 }
 
+// `aux` must have been zeroed on the stream (capi.cu does it with the fix-up counter).
 cudaError_t launch_codebook_prep(const float *W, int K, int C, const TcPlan &plan, float *wimg,
                                  CodebookAux *aux, cudaStream_t stream)
 {
-    codebook_prep_kernel<<<1, 256, 0, stream>>>(W, K, C, plan.C8, plan.nblkW, plan.Ntot, wimg, aux);
+    const int rows_per_block = 8;
+    codebook_prep_kernel<<<(plan.Ntot + rows_per_block - 1) / rows_per_block, 256, 0, stream>>>(
+        W, K, C, plan.C8, plan.nblkW, plan.Ntot, wimg, aux);
     return cudaGetLastError();
 }
 
@@ -224,10 +226,17 @@ __device__ __noinline__ double pair_dist_f64(const uint8_t *xs, const uint8_t *w
 // ------------------------------------------------------------------------------------------------
 // the kernel
 // ------------------------------------------------------------------------------------------------
-template <int SL>
-__global__ void __launch_bounds__(320, 1)
+template <int SL, int SPC, int NCH, int NG>
+__global__ void __launch_bounds__(NG * 128 + 64, 1)
 bmu_tc_kernel(const __grid_constant__ CUtensorMap tmX, const TcParams p)
 {
+    constexpr int NEPI = NG * 4;            // epilogue warps
+    constexpr int NMMA = SL * SPC;          // UMMA N
+    constexpr int NS = SPC * NCH;           // slices per tile
+    constexpr int NW = (SL + 31) / 32;      // mask words per slice
+    constexpr int NBUF = NCH == 1 ? NG : 2; // TMEM accumulator buffers
+    static_assert(NCH == 1 || NG == 2, "two chunks per tile only with two epilogue groups");
+
     extern __shared__ uint8_t smem_raw[];
     const TcPlan &pl = p.plan;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -241,47 +250,43 @@ bmu_tc_kernel(const __grid_constant__ CUtensorMap tmX, const TcParams p)
     uint8_t *ones = smem + pl.off_ones;  // 4 KiB of 1.0f: the A operand of the bias K-step
     uint8_t *xs0 = smem + pl.off_x;      // X stages
     const uint32_t bar0 = sbase + pl.off_bar;
-    const uint32_t bar_full = bar0;                          // [kMaxStages]
-    const uint32_t bar_empty = bar0 + 8u * kMaxStages;       // [kMaxStages]
-    const uint32_t bar_tfull = bar0 + 16u * kMaxStages;      // [2]
-    const uint32_t bar_tempty = bar_tfull + 16u;             // [2]
-    const uint32_t bar_w = bar_tempty + 16u;                 // codebook image landed
-    volatile uint32_t *tmem_slot = reinterpret_cast<volatile uint32_t *>(smem + pl.off_bar + 8u * (2 * kMaxStages + 5));
-    int *pair_count = reinterpret_cast<int *>(smem + pl.off_bar + 8u * (2 * kMaxStages + 6));  // [2 groups][2 parities]
-    uint16_t *cand_all = reinterpret_cast<uint16_t *>(smem + pl.off_cand);
-    uint32_t *pairs_all = reinterpret_cast<uint32_t *>(smem + pl.off_pairs);
-    float *d2_all = reinterpret_cast<float *>(smem + pl.off_d2);
+    const uint32_t bar_full = bar0;                      // [kMaxStages]
+    const uint32_t bar_empty = bar0 + 8u * kMaxStages;   // [kMaxStages]
+    const uint32_t bar_tfull = bar0 + 16u * kMaxStages;  // [4]
+    const uint32_t bar_tempty = bar_tfull + 32u;         // [4]
+    const uint32_t bar_w = bar_tempty + 32u;             // codebook image landed
+    volatile uint32_t *tmem_slot =
+        reinterpret_cast<volatile uint32_t *>(smem + pl.off_bar + 16u * kMaxStages + 72u);
 
     const int nstage = pl.nstage;
     const int64_t ntiles = p.ntiles;
 
     // ---------------------------------------------------------------- one-time setup
-    if (warp == 8 && lane == 0) {
+    if (warp == NEPI && lane == 0) {
         prefetch_tensormap(&tmX);
         for (int s = 0; s < nstage; ++s) {
             mbar_init(bar_full + 8u * s, 1);   // producer's arrive.expect_tx
             mbar_init(bar_empty + 8u * s, 4);  // one arrive per warp of the owning epilogue group
         }
-        for (int b = 0; b < 2; ++b) {
+        for (int b = 0; b < NBUF; ++b) {
             mbar_init(bar_tfull + 8u * b, 1);   // tcgen05.commit
-            mbar_init(bar_tempty + 8u * b, 4);  // one arrive per epilogue warp
+            mbar_init(bar_tempty + 8u * b, 4);  // one arrive per epilogue warp of the consumer
         }
         mbar_init(bar_w, 1);
         fence_mbar_init();
     }
-    if (warp == 9) {
+    if (warp == NEPI + 1) {
         tmem_alloc(smem_u32(const_cast<uint32_t *>(tmem_slot)), (uint32_t)pl.tmem_cols);
         tmem_relinquish();
     }
     for (int i = threadIdx.x; i < 1024; i += blockDim.x) reinterpret_cast<float *>(ones)[i] = 1.0f;
-    if (threadIdx.x < 4) pair_count[threadIdx.x] = 0;
     fence_proxy_async();  // the ones tile is read by the tensor core (async proxy)
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
 
-    if (warp == 8) {
+    if (warp == NEPI) {
         // ============================================================ TMA producer
         if (lane == 0) {
             // codebook image: linear bulk copies (image is pre-swizzled in global memory)
@@ -290,10 +295,9 @@ bmu_tc_kernel(const __grid_constant__ CUtensorMap tmX, const TcParams p)
                 const uint32_t sz = min(16384u, pl.wimg_bytes - off);
                 bulk_load(sbase + off, reinterpret_cast<const uint8_t *>(p.wimg) + off, sz, bar_w);
             }
-            int64_t it = 0;
-            for (int64_t j = blockIdx.x; j < ntiles; j += gridDim.x, ++it) {
-                const int s = (int)(it % nstage);
-                const uint32_t ph = (uint32_t)((it / nstage) & 1);
+            int s = 0;
+            uint32_t ph = 0;
+            for (int64_t j = blockIdx.x; j < ntiles; j += gridDim.x) {
                 mbar_wait(bar_empty + 8u * s, ph ^ 1u);
                 mbar_arrive_expect_tx(bar_full + 8u * s, pl.stage_bytes);
                 const int64_t tile = p.tile_first + j * p.tile_stride;
@@ -301,230 +305,292 @@ bmu_tc_kernel(const __grid_constant__ CUtensorMap tmX, const TcParams p)
                 for (int b = 0; b < pl.nblkX; ++b)
                     tma_load_2d(sbase + pl.off_x + (uint32_t)s * pl.stage_bytes + (uint32_t)b * 16384u,
                                 &tmX, bar_full + 8u * s, b * 32, row0, kEvictFirst);
+                if (++s == nstage) {
+                    s = 0;
+                    ph ^= 1u;
+                }
             }
         }
-    } else if (warp == 9) {
+    } else if (warp == NEPI + 1) {
         // ============================================================ MMA issuer
         if (lane == 0) {
-            const uint32_t idesc = umma_idesc_tf32(128, (uint32_t)pl.Nmma);
+            constexpr uint32_t idesc = umma_idesc_tf32(128, (uint32_t)NMMA);
             const uint64_t desc_ones = umma_desc_nosw(sbase + pl.off_ones, 128u, 256u);
             // bias K-step: columns C8..C8+7 of the codebook image
             const uint32_t bias_blk = (uint32_t)(pl.C8 >> 5), bias_off = (uint32_t)(pl.C8 & 31) * 4u;
+            const uint32_t wblk_bytes = (uint32_t)(NCH * NMMA) * 128u;
             mbar_wait(bar_w, 0);
-            int64_t it = 0;
-            for (int64_t j = blockIdx.x; j < ntiles; j += gridDim.x, ++it) {
-                const int s = (int)(it % nstage);
-                const uint32_t ph = (uint32_t)((it / nstage) & 1);
+            int s = 0;
+            uint32_t ph = 0;
+            uint32_t q = 0;  // accumulator-chunk counter
+            for (int64_t j = blockIdx.x; j < ntiles; j += gridDim.x) {
                 mbar_wait(bar_full + 8u * s, ph);
                 const uint32_t xs_addr = sbase + pl.off_x + (uint32_t)s * pl.stage_bytes;
-                for (int c = 0; c < pl.NCH; ++c) {
-                    const int64_t q = it * pl.NCH + c;
-                    const int buf = (int)(q & 1);
-                    const uint32_t bph = (uint32_t)((q >> 1) & 1);
+#pragma unroll
+                for (int c = 0; c < NCH; ++c, ++q) {
+                    const uint32_t buf = q % NBUF;
+                    const uint32_t bph = (q / NBUF) & 1u;
                     mbar_wait(bar_tempty + 8u * buf, bph ^ 1u);
                     tc_fence_after();
-                    const uint32_t d_tmem = tmem_base + (uint32_t)(buf * pl.Nmma);
-                    const uint32_t wrow = (uint32_t)(c * pl.Nmma) * 128u;
+                    const uint32_t d_tmem = tmem_base + buf * (uint32_t)NMMA;
+                    const uint32_t wrow = (uint32_t)(c * NMMA) * 128u;
                     for (int ks = 0; ks < pl.ksteps; ++ks) {
                         const uint32_t blk = (uint32_t)(ks >> 2), ko = (uint32_t)(ks & 3) * 32u;
                         const uint64_t da = umma_desc_sw128(xs_addr + blk * 16384u + ko);
-                        const uint64_t db =
-                            umma_desc_sw128(sbase + blk * (uint32_t)pl.Ntot * 128u + wrow + ko);
+                        const uint64_t db = umma_desc_sw128(sbase + blk * wblk_bytes + wrow + ko);
                         mma_tf32(d_tmem, da, db, idesc, ks > 0 ? 1u : 0u);
                     }
-                    const uint64_t dbias = umma_desc_sw128(
-                        sbase + bias_blk * (uint32_t)pl.Ntot * 128u + wrow + bias_off);
+                    const uint64_t dbias =
+                        umma_desc_sw128(sbase + bias_blk * wblk_bytes + wrow + bias_off);
                     mma_tf32(d_tmem, desc_ones, dbias, idesc, 1u);
                     mma_commit(bar_tfull + 8u * buf);
+                }
+                if (++s == nstage) {
+                    s = 0;
+                    ph ^= 1u;
                 }
             }
         }
     } else {
         // ============================================================ epilogue groups
-        const int g = warp >> 2;            // group 0/1
-        const int quad = warp & 3;          // TMEM lane quadrant this warp may read
-        const int row = quad * 32 + lane;   // tile row == TMEM lane
-        const int gtid = threadIdx.x & 127; // thread index within the group
-        const uint32_t bar_id = 1u + (uint32_t)g;
-        uint16_t *my_cand = cand_all + (size_t)(g * 128 + row) * kMaxCand;
-        uint32_t *pairs = pairs_all + (size_t)g * kPairCap;
-        float *d2buf = d2_all + (size_t)g * kPairCap;
-        const float wmax = p.aux->wmax, wmax2 = p.aux->wmax2;
-        const int nchunks16 = pl.C8 >> 2;   // 16-byte chunks holding real channels (C8 / 4)
+        const int g = warp >> 2;             // group
+        const int quad = warp & 3;           // TMEM lane quadrant this warp may read
+        const int row = quad * 32 + lane;    // tile row == TMEM lane
+        const uint32_t r7 = (uint32_t)(row & 7);
+        uint32_t *pairs = reinterpret_cast<uint32_t *>(smem + pl.off_pairs) + warp * (2 * kWarpPairCap);
+        float *d2buf = reinterpret_cast<float *>(pairs + kWarpPairCap);
+        const int Ntot = NCH * NMMA;
+        const int nchunks16 = pl.C8 >> 2;    // 16-byte chunks holding real channels
         const float eps32 = (float)(pl.C + 8) * 2.4e-7f;
+        const uint32_t tmem_lane = tmem_base + ((uint32_t)(quad * 32) << 16);
         unsigned long long st_flag = 0, st_pairs = 0, st_fp64 = 0, st_fix = 0;
         mbar_wait(bar_w, 0);  // codebook image visible to this thread (stages 2/3 read it)
+        const float wmax = __int_as_float(p.ctl->wmax_bits);
+        const float wmax2 = wmax * wmax;
 
-        int64_t it = g;
+        // stage / phase bookkeeping of this group's tile sequence (it = g, g+NG, ...)
+        int s = g % nstage;
+        uint32_t ph = (uint32_t)((g / nstage) & 1);
+        uint32_t use = 0;  // how many tiles this group has consumed
         for (int64_t j = (int64_t)blockIdx.x + (int64_t)g * gridDim.x; j < ntiles;
-             j += 2 * (int64_t)gridDim.x, it += 2) {
-            const int s = (int)(it % nstage);
-            const uint32_t ph = (uint32_t)((it / nstage) & 1);
+             j += (int64_t)NG * gridDim.x, ++use) {
             const uint8_t *xs = xs0 + (size_t)s * pl.stage_bytes;
             const int64_t tile = p.tile_first + j * p.tile_stride;
             const int64_t grow = tile * kTile + row;  // global row
-            const int par = (int)((it >> 1) & 1);
-            int *my_pair_count = pair_count + g * 2 + par;
 
             mbar_wait(bar_full + 8u * s, ph);  // X tile landed
 
             // ---- per-row error bound of the tf32 scores
-            float xn2 = 0.f;
-            for (int q = 0; q < nchunks16; ++q) {
-                const float4 x = *x_chunk_ptr(xs, row, q >> 3, q & 7);
-                xn2 = fmaf(x.x, x.x, xn2);
-                xn2 = fmaf(x.y, x.y, xn2);
-                xn2 = fmaf(x.z, x.z, xn2);
-                xn2 = fmaf(x.w, x.w, xn2);
+            float xn2a = 0.f, xn2b = 0.f;
+            {
+                const uint8_t *xrow = xs + (uint32_t)row * 128u;
+#pragma unroll 4
+                for (int qq = 0; qq < nchunks16; ++qq) {
+                    const float4 x = *reinterpret_cast<const float4 *>(
+                        xrow + (uint32_t)(qq >> 3) * 16384u + ((((uint32_t)qq & 7u) ^ r7) << 4));
+                    xn2a = fmaf(x.x, x.x, xn2a);
+                    xn2b = fmaf(x.y, x.y, xn2b);
+                    xn2a = fmaf(x.z, x.z, xn2a);
+                    xn2b = fmaf(x.w, x.w, xn2b);
+                }
             }
             // |score error| <= 2^-8 (1+1/16) ||x|| wmax + 2^-18 wmax^2 ; delta = 2 x that
             const float delta =
-                2.0f * (0.00415039f * sqrtf(xn2) * 1.000001f * wmax + 3.8147e-6f * wmax2);
+                2.0f * (0.00415039f * sqrtf(xn2a + xn2b) * 1.000001f * wmax + 3.8147e-6f * wmax2);
 
             float m_run = __int_as_float(0x7f800000);
-            int ncand = 0;
-            int cand0 = 0;
+            uint32_t mw[NS][NW];
+#pragma unroll
+            for (int a = 0; a < NS; ++a)
+#pragma unroll
+                for (int w = 0; w < NW; ++w) mw[a][w] = 0u;
 
-            for (int c = 0; c < pl.NCH; ++c) {
-                const int64_t q = it * pl.NCH + c;
-                const int buf = (int)(q & 1);
-                const uint32_t bph = (uint32_t)((q >> 1) & 1);
-                // With two chunks per tile both groups alternate on the same accumulator buffer, so
-                // this group may get here a whole phase early, where a parity wait would alias and
-                // fall through.  Waiting first for the previous use's release (made by the OTHER
-                // group, after it saw the previous commit) pins the barrier to the right phase.
-                if (pl.NCH > 1 && q >= 2) mbar_wait(bar_tempty + 8u * buf, bph ^ 1u);
+#pragma unroll
+            for (int c = 0; c < NCH; ++c) {
+                uint32_t buf, bph;
+                if constexpr (NCH == 1) {
+                    buf = (uint32_t)g;
+                    bph = use & 1u;
+                } else {
+                    // chunk counter q = it * 2 + c with it = g + 2 * use; buffers alternate
+                    const uint32_t q = ((uint32_t)g + 2u * use) * 2u + (uint32_t)c;
+                    buf = q & 1u;
+                    bph = (q >> 1) & 1u;
+                    // Both groups alternate on the same buffer, so this group may get here a whole
+                    // phase early, where a parity wait would alias and fall through.  Waiting first
+                    // for the previous use's release (made by the OTHER group after it saw the
+                    // previous commit) pins the barrier to the right phase.
+                    if (q >= 2) mbar_wait(bar_tempty + 8u * buf, bph ^ 1u);
+                }
                 mbar_wait(bar_tfull + 8u * buf, bph);
                 tc_fence_after();
-                for (int sidx = 0; sidx < pl.spc; ++sidx) {
+#pragma unroll
+                for (int sidx = 0; sidx < SPC; ++sidx) {
+                    const int sl = c * SPC + sidx;
                     uint32_t vr[SL];
-                    const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) +
-                                           (uint32_t)(buf * pl.Nmma + sidx * SL);
-                    tmem_ld_cols<SL>(taddr, vr);
+                    tmem_ld_cols<SL>(tmem_lane + buf * (uint32_t)NMMA + (uint32_t)(sidx * SL), vr);
                     tc_wait_ld();
-                    if (sidx == pl.spc - 1) {
+                    if (sidx == SPC - 1) {
                         // accumulator buffer fully read: hand it back to the MMA warp
                         tc_fence_before();
                         __syncwarp();
                         if (lane == 0) mbar_arrive(bar_tempty + 8u * buf);
                     }
-                    // pass 1: slice minimum
-                    float ms = __uint_as_float(vr[0]);
+                    // pass 1: slice minimum (four independent chains)
+                    float a0 = __uint_as_float(vr[0]), a1 = __uint_as_float(vr[1]);
+                    float a2 = __uint_as_float(vr[2]), a3 = __uint_as_float(vr[3]);
 #pragma unroll
-                    for (int i = 1; i < SL; ++i) ms = fminf(ms, __uint_as_float(vr[i]));
+                    for (int i = 4; i + 7 < SL; i += 8) {
+                        a0 = fminf(fminf(a0, __uint_as_float(vr[i])), __uint_as_float(vr[i + 4]));
+                        a1 = fminf(fminf(a1, __uint_as_float(vr[i + 1])), __uint_as_float(vr[i + 5]));
+                        a2 = fminf(fminf(a2, __uint_as_float(vr[i + 2])), __uint_as_float(vr[i + 6]));
+                        a3 = fminf(fminf(a3, __uint_as_float(vr[i + 3])), __uint_as_float(vr[i + 7]));
+                    }
+#pragma unroll
+                    for (int i = 4 + ((SL - 4) / 8) * 8; i < SL; ++i)
+                        a0 = fminf(a0, __uint_as_float(vr[i]));
+                    const float ms = fminf(fminf(a0, a1), fminf(a2, a3));
                     const float m_new = fminf(m_run, ms);
-                    if (m_new + delta < m_run) ncand = 0;  // earlier candidates are out of range
+                    if (sl > 0) {
+                        // earlier candidates are out of range once the minimum drops by > delta
+                        const bool drop = m_new + delta < m_run;
+#pragma unroll
+                        for (int a = 0; a < NS; ++a)
+                            if (a < sl)
+#pragma unroll
+                                for (int w = 0; w < NW; ++w) mw[a][w] = drop ? 0u : mw[a][w];
+                    }
                     m_run = m_new;
                     const float thr = m_run + delta;
-                    if (__any_sync(0xffffffffu, ms < thr)) {
-                        // pass 2: sign bit of (v - thr) funnel-shifted into a bit mask
-                        constexpr int NW = (SL + 31) / 32;
-                        uint32_t mw[NW];
-#pragma unroll
-                        for (int w = 0; w < NW; ++w) mw[w] = 0u;
+                    if (sl == 0 || __any_sync(0xffffffffu, ms < thr)) {
+                        // pass 2: sign bit of (v - thr) funnel-shifted into a bit mask; value i of
+                        // word w ends at bit (cnt_w - 1 - (i - 32 w))
 #pragma unroll
                         for (int i = 0; i < SL; ++i) {
                             const float d = __uint_as_float(vr[i]) - thr;
-                            mw[i >> 5] = __funnelshift_l(__float_as_uint(d), mw[i >> 5], 1);
-                        }
-                        const int colbase = c * pl.Nmma + sidx * SL;
-#pragma unroll
-                        for (int w = 0; w < NW; ++w) {
-                            const int cnt = (SL - 32 * w) < 32 ? (SL - 32 * w) : 32;
-                            uint32_t m = mw[w];
-                            while (m) {
-                                const int b = 31 - __clz(m);
-                                m &= ~(1u << b);
-                                const int idx = colbase + 32 * w + (cnt - 1 - b);
-                                if (ncand == 0) cand0 = idx;
-                                if (ncand < kMaxCand) my_cand[ncand] = (uint16_t)idx;
-                                ++ncand;
-                            }
+                            mw[sl][i >> 5] = __funnelshift_l(__float_as_uint(d), mw[sl][i >> 5], 1);
                         }
                     }
                 }
             }
 
             // ---- resolve
-            int label = kLabelFixup;
-            int pbase = -1;
+            int nc = 0;
+#pragma unroll
+            for (int a = 0; a < NS; ++a)
+#pragma unroll
+                for (int w = 0; w < NW; ++w) nc += __popc(mw[a][w]);
             const bool finite = fabsf(m_run) <= FLT_MAX;
-            if (finite && ncand == 1) {
-                label = cand0 + 1;
-            } else if (finite && ncand >= 2 && ncand <= kMaxCand) {
-                const int base = atomicAdd(my_pair_count, ncand);
-                if (base + ncand <= kPairCap) {
-                    pbase = base;
-                    for (int t = 0; t < ncand; ++t)
-                        pairs[base + t] = ((uint32_t)row << 16) | (uint32_t)my_cand[t];
-                    ++st_flag;
-                    st_pairs += ncand;
-                }
+            int label = kLabelFixup;
+            if (finite && nc == 1) {
+                int idx = 0;
+#pragma unroll
+                for (int a = 0; a < NS; ++a)
+#pragma unroll
+                    for (int w = 0; w < NW; ++w) {
+                        const int cnt = (SL - 32 * w) < 32 ? (SL - 32 * w) : 32;
+                        if (mw[a][w]) idx = a * SL + 32 * w + cnt - 1 - (31 - __clz(mw[a][w]));
+                    }
+                label = idx + 1;
             }
-            bar_sync(bar_id, 128);  // pairs of this tile are complete
-            if (gtid == 0) pair_count[g * 2 + (par ^ 1)] = 0;  // reset the next tile's counter
-            {
-                int P = *reinterpret_cast<volatile int *>(my_pair_count);
-                if (P > kPairCap) P = kPairCap;  // overflowing rows did not write their pairs
-                // NOTE: rows that overflowed still bumped the counter; their range is unwritten and
-                // no row owns it, so evaluating stale pairs there is harmless (indices are masked).
-                for (int pi = gtid; pi < P; pi += 128) {
+            bool flagged = finite && nc >= 2 && nc <= kMaxCand;
+            // warp-local pair list: exclusive prefix of the candidate counts of flagged lanes
+            int incl = flagged ? nc : 0;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const int t = __shfl_up_sync(0xffffffffu, incl, o);
+                if (lane >= o) incl += t;
+            }
+            int pbase = incl - (flagged ? nc : 0);
+            if (flagged && incl > kWarpPairCap) flagged = false;  // overflow: exact fix-up instead
+            const unsigned fmask = __ballot_sync(0xffffffffu, flagged);
+            if (fmask) {
+                int total = 0;  // pairs actually written: prefix of the highest flagged lane
+                {
+                    const int hi = 31 - __clz(fmask);
+                    total = __shfl_sync(0xffffffffu, incl, hi);
+                }
+                if (flagged) {
+                    int t = pbase;
+#pragma unroll
+                    for (int a = 0; a < NS; ++a)
+#pragma unroll
+                        for (int w = 0; w < NW; ++w) {
+                            const int cnt = (SL - 32 * w) < 32 ? (SL - 32 * w) : 32;
+                            uint32_t m = mw[a][w];
+                            while (m) {
+                                const int b = 31 - __clz(m);
+                                m &= ~(1u << b);
+                                pairs[t++] = ((uint32_t)row << 16) |
+                                             (uint32_t)(a * SL + 32 * w + cnt - 1 - b);
+                            }
+                        }
+                    ++st_flag;
+                    st_pairs += nc;
+                }
+                __syncwarp();
+                // stage 2: fp32 distances of the warp's pairs, one pair per lane and pass.
+                // (lanes whose flagged neighbours overflowed leave holes; holes are never read.)
+                for (int pi = lane; pi < total; pi += 32) {
                     const uint32_t pr = pairs[pi];
                     const int prow = (int)(pr >> 16) & 127;
                     int pnode = (int)(pr & 0xFFFFu);
-                    if (pnode >= pl.Ntot) pnode = 0;
-                    d2buf[pi] = pair_dist2_f32(xs, ws, pl.Ntot, nchunks16, prow, pnode);
+                    if (pnode >= Ntot) pnode = 0;
+                    d2buf[pi] = pair_dist2_f32(xs, ws, Ntot, nchunks16, prow, pnode);
                 }
-            }
-            bar_sync(bar_id, 128);  // stage-2 distances are complete
-            if (pbase >= 0) {
-                float best = __int_as_float(0x7f800000);
-                for (int t = 0; t < ncand; ++t) best = fminf(best, d2buf[pbase + t]);
-                const float bound = best * (1.0f + eps32) + 1.0e-30f;
-                int nsurv = 0, surv0 = -1;
-                for (int t = 0; t < ncand; ++t)
-                    if (d2buf[pbase + t] <= bound) {
-                        if (nsurv == 0) surv0 = (int)my_cand[t];
-                        ++nsurv;
-                    }
-                if (nsurv == 1 && surv0 < pl.K) {
-                    label = surv0 + 1;
-                } else if (nsurv >= 2) {
-                    // stage 3: fp64 replica of the reference loop over the survivors, index order
-                    ++st_fp64;
-                    double bestd = DBL_MAX;
-                    int bestk = -1;
-                    for (int t = 0; t < ncand; ++t) {
-                        if (!(d2buf[pbase + t] <= bound)) continue;
-                        const int k = (int)my_cand[t];
-                        if (k >= pl.K) continue;
-                        const double d = pair_dist_f64(xs, ws, pl.Ntot, pl.C, row, k);
-                        if (d < bestd) {
-                            bestd = d;
-                            bestk = k;
+                __syncwarp();
+                if (flagged) {
+                    float best = __int_as_float(0x7f800000);
+                    for (int t = 0; t < nc; ++t) best = fminf(best, d2buf[pbase + t]);
+                    const float bound = best * (1.0f + eps32) + 1.0e-30f;
+                    int nsurv = 0, surv0 = -1;
+                    for (int t = 0; t < nc; ++t)
+                        if (d2buf[pbase + t] <= bound) {
+                            if (nsurv == 0) surv0 = (int)(pairs[pbase + t] & 0xFFFFu);
+                            ++nsurv;
                         }
+                    if (nsurv == 1 && surv0 < pl.K) {
+                        label = surv0 + 1;
+                    } else if (nsurv >= 2) {
+                        // stage 3: fp64 replica of the reference loop over the survivors, in node
+                        // index order (pairs were written in ascending node order)
+                        ++st_fp64;
+                        double bestd = DBL_MAX;
+                        int bestk = -1;
+                        for (int t = 0; t < nc; ++t) {
+                            if (!(d2buf[pbase + t] <= bound)) continue;
+                            const int k = (int)(pairs[pbase + t] & 0xFFFFu);
+                            if (k >= pl.K) continue;
+                            const double d = pair_dist_f64(xs, ws, Ntot, pl.C, row, k);
+                            if (d < bestd) {
+                                bestd = d;
+                                bestk = k;
+                            }
+                        }
+                        label = bestk >= 0 ? bestk + 1 : kLabelFixup;
                     }
-                    label = bestk >= 0 ? bestk + 1 : kLabelFixup;
                 }
+                __syncwarp();  // pair buffers are reused by the next tile
             }
-            if (label == kLabelFixup || label > pl.K) {
-                label = kLabelFixup;
-                if (grow < p.n) {
-                    ++st_fix;
-                    atomicAdd(p.fixup_count, 1);
-                }
-            }
+            if (label > pl.K) label = kLabelFixup;  // a padded codebook row can only win on garbage
             if (grow < p.n) {
-                if (p.compact_labels)
-                    p.labels[j * kTile + row] = label;
-                else
-                    p.labels[grow] = label;
+                if (label == kLabelFixup) {
+                    ++st_fix;
+                    atomicAdd(&p.ctl->fixup_count, 1);
+                }
+                p.labels[p.compact_labels ? j * kTile + row : grow] = label;
             } else if (p.compact_labels) {
                 p.labels[j * kTile + row] = 0;  // padding row of the last tile: never counted
             }
-            // all reads of this X stage (and of the pair buffers) by this warp are done
+            // all reads of this X stage by this warp are done
             __syncwarp();
             if (lane == 0) mbar_arrive(bar_empty + 8u * s);
+            // next tile of this group: NG stages further
+            s += NG;
+            if (s >= nstage) {
+                s -= nstage;
+                ph ^= 1u;
+            }
         }
 
         if (p.stats) {
@@ -546,21 +612,21 @@ bmu_tc_kernel(const __grid_constant__ CUtensorMap tmX, const TcParams p)
     // ---------------------------------------------------------------- teardown
     tc_fence_before();
     __syncthreads();
-    if (warp == 9) {
+    if (warp == NEPI + 1) {
         tc_fence_after();
         tmem_dealloc(tmem_base, (uint32_t)pl.tmem_cols);
     }
 }
 
-template <int SL>
+template <int SL, int SPC, int NCH, int NG>
 static cudaError_t launch_one(const CUtensorMap &tmX, const TcParams &p, int grid,
                               cudaStream_t stream)
 {
-    cudaError_t e = cudaFuncSetAttribute(bmu_tc_kernel<SL>,
+    cudaError_t e = cudaFuncSetAttribute(bmu_tc_kernel<SL, SPC, NCH, NG>,
                                          cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          (int)p.plan.smem_bytes);
     if (e != cudaSuccess) return e;
-    bmu_tc_kernel<SL><<<grid, 320, p.plan.smem_bytes, stream>>>(tmX, p);
+    bmu_tc_kernel<SL, SPC, NCH, NG><<<grid, NG * 128 + 64, p.plan.smem_bytes, stream>>>(tmX, p);
     return cudaGetLastError();
 }
 
@@ -570,16 +636,28 @@ cudaError_t launch_bmu_tc(const CUtensorMap &tmX, const TcParams &p, int num_sms
     if (p.ntiles <= 0) return cudaSuccess;
     int grid = num_sms;
     if ((int64_t)grid > p.ntiles) grid = (int)p.ntiles;
-    switch (p.plan.SL) {
-        case 32: return launch_one<32>(tmX, p, grid, stream);
-        case 64: return launch_one<64>(tmX, p, grid, stream);
-        case 80: return launch_one<80>(tmX, p, grid, stream);
-        case 96: return launch_one<96>(tmX, p, grid, stream);
-        case 104: return launch_one<104>(tmX, p, grid, stream);
-        case 112: return launch_one<112>(tmX, p, grid, stream);
-        case 128: return launch_one<128>(tmX, p, grid, stream);
-        default: return cudaErrorInvalidValue;
-    }
+    const TcPlan &pl = p.plan;
+#define PIXIE_VARIANT(a_, b_, c_, d_)                                 \
+    if (pl.SL == a_ && pl.spc == b_ && pl.NCH == c_ && pl.NG == d_)   \
+        return launch_one<a_, b_, c_, d_>(tmX, p, grid, stream);
+    PIXIE_VARIANT(32, 1, 1, 4)
+    PIXIE_VARIANT(32, 2, 1, 4)
+    PIXIE_VARIANT(48, 2, 1, 4)
+    PIXIE_VARIANT(56, 2, 1, 4)
+    PIXIE_VARIANT(64, 2, 1, 4)
+    PIXIE_VARIANT(32, 1, 1, 2)
+    PIXIE_VARIANT(32, 2, 1, 2)
+    PIXIE_VARIANT(48, 2, 1, 2)
+    PIXIE_VARIANT(56, 2, 1, 2)
+    PIXIE_VARIANT(64, 2, 1, 2)
+    PIXIE_VARIANT(80, 2, 1, 2)
+    PIXIE_VARIANT(104, 2, 1, 2)
+    PIXIE_VARIANT(128, 2, 1, 2)
+    PIXIE_VARIANT(80, 2, 2, 2)
+    PIXIE_VARIANT(104, 2, 2, 2)
+    PIXIE_VARIANT(128, 2, 2, 2)
+#undef PIXIE_VARIANT
+    return cudaErrorInvalidValue;
 }
 
 }  // namespace pixie

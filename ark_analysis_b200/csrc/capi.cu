@@ -91,7 +91,6 @@ int num_sms_current_device()
 struct Workspace {
     float *wimg;
     CodebookAux *aux;
-    int *fixup_count;
     float *partials;
     int32_t *labels_scratch;
     size_t total;
@@ -105,8 +104,6 @@ Workspace carve(void *base, int64_t n_visit, int C, int K)
     w.wimg = reinterpret_cast<float *>((char *)base + off);
     off += align_up(wimg_max, 1024);
     w.aux = reinterpret_cast<CodebookAux *>((char *)base + off);
-    off += 256;
-    w.fixup_count = reinterpret_cast<int *>((char *)base + off);
     off += 256;
     w.partials = reinterpret_cast<float *>((char *)base + off);
     off += align_up((size_t)kSumParts * K * (C + 1) * sizeof(float), 256);
@@ -139,7 +136,7 @@ int bmu_tiles(const float *X, int64_t n, int C, int64_t ldX, const float *W, int
         }
         return PIXIE_OK;
     }
-    PX_CUDA(cudaMemsetAsync(ws.fixup_count, 0, sizeof(int), stream));
+    PX_CUDA(cudaMemsetAsync(ws.aux, 0, sizeof(CodebookAux), stream));
     PX_CUDA(launch_codebook_prep(W, K, C, plan, ws.wimg, ws.aux, stream));
     TcParams p{};
     p.n = n;
@@ -147,17 +144,16 @@ int bmu_tiles(const float *X, int64_t n, int C, int64_t ldX, const float *W, int
     p.tile_stride = tile_stride;
     p.ntiles = ntiles;
     p.wimg = ws.wimg;
-    p.aux = ws.aux;
     p.labels = labels;
     p.compact_labels = compact;
     p.stats = stats;
-    p.fixup_count = ws.fixup_count;
+    p.ctl = ws.aux;
     p.plan = plan;
     PX_CUDA(launch_bmu_tc(tm, p, num_sms_current_device(), stream));
     // rows the tensor-core kernel could not settle (NaN/Inf rows, degenerate codebooks): exact
     // kernel; returns immediately when the counter is zero.
     PX_CUDA(launch_bmu_exact(X, n, C, ldX, W, K, labels, tile_first, tile_stride, ntiles, compact,
-                             ws.fixup_count, stream));
+                             &ws.aux->fixup_count, stream));
     if (stats) {
         set_u64_kernel<<<1, 1, 0, stream>>>(stats + PIXIE_STAT_KERNEL, 1ull);
     }

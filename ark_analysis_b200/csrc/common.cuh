@@ -13,14 +13,14 @@ namespace pixie {
 constexpr int kTile = PIXIE_TILE;  // rows per tile == UMMA M == TMEM lanes
 constexpr int kLabelFixup = -1;    // sentinel: row must be resolved by the exact fix-up kernel
 constexpr int kMaxCand = 16;       // candidate nodes kept per row before giving up to the fix-up
-constexpr int kPairCap = 1024;     // (row, node) pairs re-evaluated per tile and epilogue group
-constexpr int kMaxStages = 6;
+constexpr int kWarpPairCap = 128;  // (row, node) pairs re-evaluated per tile by one epilogue warp
+constexpr int kMaxStages = 8;
 
 // Device-side result of the codebook preparation kernel, read by the BMU kernel.
 struct CodebookAux {
-    float wmax;   // max_k ||w_k||   (inflated by a few ulp)
-    float wmax2;  // wmax^2
+    int wmax_bits;  // float bits of max_k ||w_k|| (atomicMax on the non-negative float pattern)
     int nonfinite;
+    int fixup_count;  // rows the tensor-core kernel handed to the exact fix-up kernel
     int pad;
 };
 
@@ -32,16 +32,17 @@ struct TcPlan {
     int ksteps;  // C8 / 8 data K-steps (+1 bias K-step)
     int nblkX;   // 32-channel (128-byte) blocks of one X tile  = ceil(C / 32)
     int nblkW;   // 32-column blocks of the codebook image      = ceil((C8 + 8) / 32)
-    int SL;      // TMEM columns per epilogue slice (template parameter of the kernel)
-    int spc;     // slices per accumulator chunk
-    int NCH;     // accumulator chunks per tile (1 or 2)
+    int SL;      // TMEM columns per epilogue slice            (template parameter)
+    int spc;     // slices per accumulator chunk               (template parameter)
+    int NCH;     // accumulator chunks per tile, 1 or 2        (template parameter)
+    int NG;      // epilogue groups of 4 warps, 2 or 4         (template parameter)
     int Nmma;    // UMMA N = SL * spc (multiple of 16, <= 256)
     int Ntot;    // NCH * Nmma >= K: codebook rows in the image (padded rows never win)
-    int nbuf;    // TMEM accumulator buffers (2)
+    int nbuf;    // TMEM accumulator buffers: NG when NCH == 1, else 2
     int tmem_cols;
-    int nstage;  // X tile pipeline depth
+    int nstage;  // X tile pipeline depth (multiple of NG)
     uint32_t stage_bytes, wimg_bytes;
-    uint32_t off_ones, off_x, off_bar, off_cand, off_pairs, off_d2;
+    uint32_t off_ones, off_x, off_bar, off_pairs;
     uint32_t smem_bytes;  // dynamic shared memory to request (includes 1 KiB alignment slack)
 };
 
@@ -53,11 +54,10 @@ struct TcParams {
     int64_t tile_stride;   // distance between visited tiles
     int64_t ntiles;        // number of tiles visited by this launch
     const float *wimg;     // prepared codebook image (global)
-    const CodebookAux *aux;
     int32_t *labels;       // labels[row] (assign) or labels[j * 128 + r] (compact, accum)
     int compact_labels;
     unsigned long long *stats;  // may be null
-    int *fixup_count;           // device counter of sentinel rows
+    CodebookAux *ctl;           // fixup_count lives here
     TcPlan plan;
 };
 
