@@ -43,9 +43,10 @@ struct Variant {
 };
 // every entry has a template instantiation in launch_bmu_tc()
 const Variant kVariants[] = {
-    {32, 1, 1, 4}, {32, 2, 1, 4}, {48, 2, 1, 4}, {56, 2, 1, 4}, {64, 2, 1, 4},
-    {32, 1, 1, 2}, {32, 2, 1, 2}, {48, 2, 1, 2}, {56, 2, 1, 2}, {64, 2, 1, 2},
-    {80, 2, 1, 2}, {104, 2, 1, 2}, {128, 2, 1, 2}, {80, 2, 2, 2}, {104, 2, 2, 2}, {128, 2, 2, 2},
+    {32, 1, 1, 4}, {32, 2, 1, 4}, {48, 2, 1, 4}, {50, 2, 1, 4}, {56, 2, 1, 4}, {64, 2, 1, 4},
+    {32, 1, 1, 2}, {32, 2, 1, 2}, {48, 2, 1, 2}, {50, 2, 1, 2}, {56, 2, 1, 2}, {64, 2, 1, 2},
+    {80, 2, 1, 2}, {100, 2, 1, 2}, {104, 2, 1, 2}, {128, 2, 1, 2},
+    {80, 2, 2, 2}, {100, 2, 2, 2}, {104, 2, 2, 2}, {128, 2, 2, 2},
 };
 }  // namespace
 
@@ -67,9 +68,11 @@ TcPlan make_tc_plan(int C, int K)
         p.spc = v.spc;
         p.NCH = v.NCH;
         p.NG = v.NG;
-        p.Nmma = v.SL * v.spc;
-        p.Ntot = p.Nmma * v.NCH;
-        if (p.Ntot < K) continue;
+        p.Nchunk = v.SL * v.spc;
+        if (v.NCH > 1 && p.Nchunk % 8) continue;  // chunk base must stay on a swizzle-atom row
+        p.Nmma = (p.Nchunk + 15) / 16 * 16;
+        p.Ntot = (v.NCH - 1) * p.Nchunk + p.Nmma;
+        if (p.Nchunk * v.NCH < K) continue;
         p.nbuf = v.NCH == 1 ? v.NG : 2;
         const int need = p.nbuf * p.Nmma;
         if (need > 512) continue;
@@ -92,7 +95,7 @@ TcPlan make_tc_plan(int C, int K)
         p.smem_bytes = p.off_pairs + (uint32_t)(4 * v.NG) * kWarpPairCap * 8u + 1024u;
         p.ok = true;
         // fewest padded codebook rows first; then more epilogue groups; then deeper pipeline
-        const long cost = (long)p.Ntot * 1000 - v.NG * 10 - p.nstage;
+        const long cost = (long)(p.Nchunk * v.NCH) * 1000 - v.NG * 10 - p.nstage;
         if (best_cost < 0 || cost < best_cost) {
             best_cost = cost;
             best = p;
@@ -127,12 +130,13 @@ codebook_prep_kernel(const float *__restrict__ W, int K, int C, int C8, int nblk
     const int ncols = nblkW * 32;
     char *base = reinterpret_cast<char *>(wimg);
     double nrm2 = 0.0;
-    bool bad = false;
+    bool bad = false, neg = false;
     for (int col = lane; col < ncols; col += 32) {
         float v = 0.f;
         if (row < K && col < C) {
             const float w = W[(size_t)row * C + col];
             if (!(fabsf(w) <= FLT_MAX)) bad = true;
+            if (__float_as_int(w) < 0) neg = true;  // sign bit set (includes -0.0: conservative)
             nrm2 += (double)w * (double)w;
             v = -2.0f * w;
         }
@@ -141,6 +145,7 @@ codebook_prep_kernel(const float *__restrict__ W, int K, int C, int C8, int nblk
     }
     for (int o = 16; o > 0; o >>= 1) nrm2 += __shfl_xor_sync(~0u, nrm2, o);
     bad = __any_sync(~0u, bad);
+    neg = __any_sync(~0u, neg);
     if (lane == 0) {
         float bias = (row < K) ? (float)nrm2 : 1.0e30f;
         if (!(bias <= FLT_MAX)) bias = FLT_MAX;  // overflowed norms: row can never win anyway
@@ -154,6 +159,7 @@ codebook_prep_kernel(const float *__restrict__ W, int K, int C, int C8, int nblk
         *reinterpret_cast<float *>(base + img_offset(Ntot, row, C8 + 2)) = l;
         if (row < K) {
             if (bad) atomicOr(&aux->nonfinite, 1);
+            if (neg) atomicOr(&aux->w_has_negative, 1);
             float nr = (float)sqrt(nrm2) * 1.0000005f;
             if (!(nr <= FLT_MAX)) nr = FLT_MAX;
             atomicMax(&aux->wmax_bits, __float_as_int(nr));  // non-negative floats order as ints
@@ -174,7 +180,8 @@ cudaError_t launch_codebook_prep(const float *W, int K, int C, const TcPlan &pla
 // ------------------------------------------------------------------------------------------------
 // device helpers shared by the epilogue stages
 // ------------------------------------------------------------------------------------------------
-// fp32 value of channel `col` of tile row `row` in an X stage (TMA SWIZZLE_128B layout).
+// Both the X stages (written by TMA SWIZZLE_128B) and the codebook image keep logical 16-byte
+// chunk c of row r of a 32-column block at physical chunk (c ^ (r & 7)).
 __device__ __forceinline__ const float4 *x_chunk_ptr(const uint8_t *xs, int row, int blk, int chunk)
 {
     return reinterpret_cast<const float4 *>(xs + (size_t)blk * 16384u + (size_t)row * 128u +
@@ -188,22 +195,50 @@ __device__ __forceinline__ const float4 *w_chunk_ptr(const uint8_t *ws, int Ntot
                                             (size_t)(((chunk ^ (node & 7)) & 7) << 4));
 }
 
+// acc += (x + 0.5 w')^2 over one 16-byte chunk, packed fp32 (w' = -2 w, so x + 0.5 w' = x - w)
+__device__ __forceinline__ void dist2_chunk(const float4 x, const float4 w, uint64_t half2,
+                                            uint64_t &acc0, uint64_t &acc1)
+{
+    const uint64_t d0 = fma2(pack2(w.x, w.y), half2, pack2(x.x, x.y));
+    const uint64_t d1 = fma2(pack2(w.z, w.w), half2, pack2(x.z, x.w));
+    acc0 = fma2(d0, d0, acc0);
+    acc1 = fma2(d1, d1, acc1);
+}
+
 // stage 2: fp32 squared distance between tile row `row` and codebook node `node`.
+// Full 32-channel blocks are walked in PHYSICAL chunk order (the sum does not care about order):
+// physical X chunk pc holds logical chunk pc ^ (row & 7), which sits in the codebook row at
+// physical chunk pc ^ (row & 7) ^ (node & 7) -- one XOR per chunk, no per-operand swizzle math.
+// The last, partial block is walked logically so the bias columns of the image are never read.
 __device__ __forceinline__ float pair_dist2_f32(const uint8_t *xs, const uint8_t *ws, int Ntot,
                                                 int nchunks16, int row, int node)
 {
-    float acc0 = 0.f, acc1 = 0.f;
-    for (int q = 0; q < nchunks16; ++q) {
-        const float4 x = *x_chunk_ptr(xs, row, q >> 3, q & 7);
-        const float4 w = *w_chunk_ptr(ws, Ntot, node, q >> 3, q & 7);
-        const float d0 = fmaf(0.5f, w.x, x.x), d1 = fmaf(0.5f, w.y, x.y);  // x - w, w = -0.5 w'
-        const float d2 = fmaf(0.5f, w.z, x.z), d3 = fmaf(0.5f, w.w, x.w);
-        acc0 = fmaf(d0, d0, acc0);
-        acc1 = fmaf(d1, d1, acc1);
-        acc0 = fmaf(d2, d2, acc0);
-        acc1 = fmaf(d3, d3, acc1);
+    const uint64_t half2 = pack2(0.5f, 0.5f);
+    uint64_t acc0 = 0ull, acc1 = 0ull;
+    const int nfull = nchunks16 >> 3;
+    const uint32_t t = (uint32_t)((row ^ node) & 7);
+    const uint8_t *xrow = xs + (uint32_t)row * 128u;
+    const uint8_t *wrow = ws + (uint32_t)node * 128u;
+    for (int b = 0; b < nfull; ++b) {
+#pragma unroll
+        for (uint32_t pc = 0; pc < 8; ++pc) {
+            const float4 x = *reinterpret_cast<const float4 *>(xrow + (pc << 4));
+            const float4 w = *reinterpret_cast<const float4 *>(wrow + ((pc ^ t) << 4));
+            dist2_chunk(x, w, half2, acc0, acc1);
+        }
+        xrow += 16384u;
+        wrow += (uint32_t)Ntot * 128u;
     }
-    return acc0 + acc1;
+    const int rem = nchunks16 & 7;
+    for (int lc = 0; lc < rem; ++lc) {
+        const float4 x = *x_chunk_ptr(xs, row, nfull, lc);
+        const float4 w = *w_chunk_ptr(ws, Ntot, node, nfull, lc);
+        dist2_chunk(x, w, half2, acc0, acc1);
+    }
+    float a, b, c, d;
+    unpack2(acc0, a, b);
+    unpack2(acc1, c, d);
+    return (a + b) + (c + d);
 }
 
 // stage 3: the reference's fp64 operation sequence for one (row, node) pair
@@ -231,7 +266,9 @@ __global__ void __launch_bounds__(NG * 128 + 64, 1)
 bmu_tc_kernel(const __grid_constant__ CUtensorMap tmX, const TcParams p)
 {
     constexpr int NEPI = NG * 4;            // epilogue warps
-    constexpr int NMMA = SL * SPC;          // UMMA N
+    constexpr int NCHUNK = SL * SPC;        // codebook rows per accumulator chunk
+    constexpr int NMMA = (NCHUNK + 15) / 16 * 16;  // UMMA N (columns past NCHUNK are never read)
+    static_assert(NCH == 1 || NCHUNK % 8 == 0, "chunk base must stay on a swizzle-atom row");
     constexpr int NS = SPC * NCH;           // slices per tile
     constexpr int NW = (SL + 31) / 32;      // mask words per slice
     constexpr int NBUF = NCH == 1 ? NG : 2; // TMEM accumulator buffers
@@ -318,7 +355,7 @@ bmu_tc_kernel(const __grid_constant__ CUtensorMap tmX, const TcParams p)
             const uint64_t desc_ones = umma_desc_nosw(sbase + pl.off_ones, 128u, 256u);
             // bias K-step: columns C8..C8+7 of the codebook image
             const uint32_t bias_blk = (uint32_t)(pl.C8 >> 5), bias_off = (uint32_t)(pl.C8 & 31) * 4u;
-            const uint32_t wblk_bytes = (uint32_t)(NCH * NMMA) * 128u;
+            const uint32_t wblk_bytes = (uint32_t)((NCH - 1) * NCHUNK + NMMA) * 128u;
             mbar_wait(bar_w, 0);
             int s = 0;
             uint32_t ph = 0;
@@ -333,7 +370,7 @@ bmu_tc_kernel(const __grid_constant__ CUtensorMap tmX, const TcParams p)
                     mbar_wait(bar_tempty + 8u * buf, bph ^ 1u);
                     tc_fence_after();
                     const uint32_t d_tmem = tmem_base + buf * (uint32_t)NMMA;
-                    const uint32_t wrow = (uint32_t)(c * NMMA) * 128u;
+                    const uint32_t wrow = (uint32_t)(c * NCHUNK) * 128u;
                     for (int ks = 0; ks < pl.ksteps; ++ks) {
                         const uint32_t blk = (uint32_t)(ks >> 2), ko = (uint32_t)(ks & 3) * 32u;
                         const uint64_t da = umma_desc_sw128(xs_addr + blk * 16384u + ko);
@@ -359,44 +396,66 @@ bmu_tc_kernel(const __grid_constant__ CUtensorMap tmX, const TcParams p)
         const uint32_t r7 = (uint32_t)(row & 7);
         uint32_t *pairs = reinterpret_cast<uint32_t *>(smem + pl.off_pairs) + warp * (2 * kWarpPairCap);
         float *d2buf = reinterpret_cast<float *>(pairs + kWarpPairCap);
-        const int Ntot = NCH * NMMA;
+        constexpr int Ntot = (NCH - 1) * NCHUNK + NMMA;
         const int nchunks16 = pl.C8 >> 2;    // 16-byte chunks holding real channels
         const float eps32 = (float)(pl.C + 8) * 2.4e-7f;
         const uint32_t tmem_lane = tmem_base + ((uint32_t)(quad * 32) << 16);
-        unsigned long long st_flag = 0, st_pairs = 0, st_fp64 = 0, st_fix = 0;
+        uint32_t st_flag = 0, st_pairs = 0, st_fp64 = 0, st_fix = 0;
         mbar_wait(bar_w, 0);  // codebook image visible to this thread (stages 2/3 read it)
         const float wmax = __int_as_float(p.ctl->wmax_bits);
         const float wmax2 = wmax * wmax;
+        const bool w_nonneg = p.ctl->w_has_negative == 0;
 
         // stage / phase bookkeeping of this group's tile sequence (it = g, g+NG, ...)
         int s = g % nstage;
         uint32_t ph = (uint32_t)((g / nstage) & 1);
         uint32_t use = 0;  // how many tiles this group has consumed
-        for (int64_t j = (int64_t)blockIdx.x + (int64_t)g * gridDim.x; j < ntiles;
-             j += (int64_t)NG * gridDim.x, ++use) {
-            const uint8_t *xs = xs0 + (size_t)s * pl.stage_bytes;
-            const int64_t tile = p.tile_first + j * p.tile_stride;
-            const int64_t grow = tile * kTile + row;  // global row
+        const int64_t j0 = (int64_t)blockIdx.x + (int64_t)g * gridDim.x;
+        const int64_t jstep = (int64_t)NG * gridDim.x;
+        int64_t grow = (p.tile_first + j0 * p.tile_stride) * kTile + row;  // global row
+        const int64_t grow_step = jstep * p.tile_stride * kTile;
+        int32_t *lab_ptr = p.labels + (p.compact_labels ? j0 * kTile + row : grow);
+        const int64_t lab_step = p.compact_labels ? jstep * kTile : grow_step;
+        for (int64_t j = j0; j < ntiles; j += jstep, ++use, grow += grow_step, lab_ptr += lab_step) {
+            const uint8_t *xs = xs0 + (uint32_t)s * pl.stage_bytes;
 
             mbar_wait(bar_full + 8u * s, ph);  // X tile landed
 
-            // ---- per-row error bound of the tf32 scores
-            float xn2a = 0.f, xn2b = 0.f;
+            // ---- per-row error bound of the tf32 scores.  ||x||^2 and the
+            // sign test read whole 128-byte rows in physical order: channels past C are zero-filled
+            // by TMA, and neither a sum of squares nor an OR of sign bits cares about chunk order.
+            uint64_t xa = 0ull, xb = 0ull;
+            uint32_t sgn = 0u;
             {
-                const uint8_t *xrow = xs + (uint32_t)row * 128u;
-#pragma unroll 4
-                for (int qq = 0; qq < nchunks16; ++qq) {
-                    const float4 x = *reinterpret_cast<const float4 *>(
-                        xrow + (uint32_t)(qq >> 3) * 16384u + ((((uint32_t)qq & 7u) ^ r7) << 4));
-                    xn2a = fmaf(x.x, x.x, xn2a);
-                    xn2b = fmaf(x.y, x.y, xn2b);
-                    xn2a = fmaf(x.z, x.z, xn2a);
-                    xn2b = fmaf(x.w, x.w, xn2b);
+                // Lane i starts at physical chunk (i & 7) and walks chunks (i & 7) ^ pc, so the 8
+                // lanes of a quarter-warp always hit 8 different 16-byte bank groups (reading
+                // chunk pc from every row would be an 8-way bank conflict).
+                uint32_t xaddr = sbase + pl.off_x + (uint32_t)s * pl.stage_bytes +
+                                 (uint32_t)row * 128u + (r7 << 4);
+                for (int b = 0; b < pl.nblkX; ++b, xaddr += 16384u) {
+#pragma unroll
+                    for (uint32_t pc = 0; pc < 8; ++pc) {
+                        const uint4 x = lds128(xaddr ^ (pc << 4));
+                        const uint64_t lo = pack2u(x.x, x.y), hi = pack2u(x.z, x.w);
+                        xa = fma2(lo, lo, xa);
+                        xb = fma2(hi, hi, xb);
+                        sgn |= (x.x | x.y) | (x.z | x.w);
+                    }
                 }
             }
-            // |score error| <= 2^-8 (1+1/16) ||x|| wmax + 2^-18 wmax^2 ; delta = 2 x that
-            const float delta =
-                2.0f * (0.00415039f * sqrtf(xn2a + xn2b) * 1.000001f * wmax + 3.8147e-6f * wmax2);
+            float xn2;
+            {
+                float a, b, c, d;
+                unpack2(xa, a, b);
+                unpack2(xb, c, d);
+                xn2 = (a + b) + (c + d);
+            }
+            // |score error| <= E = 2^-8 (1 + 1/16) ||x|| wmax + 2^-18 wmax^2.  In general the error
+            // is two-sided and a node can only be the true minimum if its score is within 2E of
+            // the smallest one.  When x and the codebook are both non-negative, operand truncation
+            // can only RAISE a score (by at most E), so E suffices.
+            const float E = 0.00415039f * sqrtf(xn2) * 1.000001f * wmax + 3.8147e-6f * wmax2;
+            const float delta = (w_nonneg && (int32_t)sgn >= 0) ? 1.03125f * E : 2.0f * E;
 
             float m_run = __int_as_float(0x7f800000);
             uint32_t mw[NS][NW];
@@ -465,10 +524,13 @@ bmu_tc_kernel(const __grid_constant__ CUtensorMap tmX, const TcParams p)
                     if (sl == 0 || __any_sync(0xffffffffu, ms < thr)) {
                         // pass 2: sign bit of (v - thr) funnel-shifted into a bit mask; value i of
                         // word w ends at bit (cnt_w - 1 - (i - 32 w))
+                        const uint64_t thr2 = pack2(thr, thr);
 #pragma unroll
-                        for (int i = 0; i < SL; ++i) {
-                            const float d = __uint_as_float(vr[i]) - thr;
-                            mw[sl][i >> 5] = __funnelshift_l(__float_as_uint(d), mw[sl][i >> 5], 1);
+                        for (int i = 0; i < SL; i += 2) {
+                            uint32_t d0, d1;
+                            unpack2u(sub2(pack2u(vr[i], vr[i + 1]), thr2), d0, d1);  // FADD2
+                            mw[sl][i >> 5] = __funnelshift_l(d0, mw[sl][i >> 5], 1);
+                            mw[sl][(i + 1) >> 5] = __funnelshift_l(d1, mw[sl][(i + 1) >> 5], 1);
                         }
                     }
                 }
@@ -489,27 +551,27 @@ bmu_tc_kernel(const __grid_constant__ CUtensorMap tmX, const TcParams p)
 #pragma unroll
                     for (int w = 0; w < NW; ++w) {
                         const int cnt = (SL - 32 * w) < 32 ? (SL - 32 * w) : 32;
-                        if (mw[a][w]) idx = a * SL + 32 * w + cnt - 1 - (31 - __clz(mw[a][w]));
+                        if (mw[a][w]) idx = a * SL + 32 * w + cnt - 32 + __clz(mw[a][w]);
                     }
                 label = idx + 1;
             }
-            bool flagged = finite && nc >= 2 && nc <= kMaxCand;
-            // warp-local pair list: exclusive prefix of the candidate counts of flagged lanes
-            int incl = flagged ? nc : 0;
-#pragma unroll
-            for (int o = 1; o < 32; o <<= 1) {
-                const int t = __shfl_up_sync(0xffffffffu, incl, o);
-                if (lane >= o) incl += t;
-            }
-            int pbase = incl - (flagged ? nc : 0);
-            if (flagged && incl > kWarpPairCap) flagged = false;  // overflow: exact fix-up instead
-            const unsigned fmask = __ballot_sync(0xffffffffu, flagged);
-            if (fmask) {
-                int total = 0;  // pairs actually written: prefix of the highest flagged lane
-                {
-                    const int hi = 31 - __clz(fmask);
-                    total = __shfl_sync(0xffffffffu, incl, hi);
-                }
+            bool flagged = finite && nc >= 2 && nc <= kMaxCand;  // kMaxCand <= 15
+            const unsigned fmask0 = __ballot_sync(0xffffffffu, flagged);
+            if (fmask0) {
+                // warp-local pair list: exclusive prefix of the candidate counts (<= 15, four bits)
+                // of the flagged lanes from four ballots -- no dependent shuffle chain
+                const int cntf = flagged ? nc : 0;
+                const unsigned lt = (1u << lane) - 1u;
+                const unsigned b0 = __ballot_sync(0xffffffffu, cntf & 1);
+                const unsigned b1 = __ballot_sync(0xffffffffu, cntf & 2);
+                const unsigned b2 = __ballot_sync(0xffffffffu, cntf & 4);
+                const unsigned b3 = __ballot_sync(0xffffffffu, cntf & 8);
+                const int pbase = __popc(b0 & lt) + 2 * __popc(b1 & lt) + 4 * __popc(b2 & lt) +
+                                  8 * __popc(b3 & lt);
+                if (flagged && pbase + nc > kWarpPairCap) flagged = false;  // overflow: fix-up
+                // slots [0, total) hold every pair that was written (overflowed lanes leave holes)
+                int total = __popc(b0) + 2 * __popc(b1) + 4 * __popc(b2) + 8 * __popc(b3);
+                if (total > kWarpPairCap) total = kWarpPairCap;
                 if (flagged) {
                     int t = pbase;
 #pragma unroll
@@ -519,18 +581,18 @@ bmu_tc_kernel(const __grid_constant__ CUtensorMap tmX, const TcParams p)
                             const int cnt = (SL - 32 * w) < 32 ? (SL - 32 * w) : 32;
                             uint32_t m = mw[a][w];
                             while (m) {
-                                const int b = 31 - __clz(m);
-                                m &= ~(1u << b);
+                                const int lz = __clz(m);
+                                m &= ~(0x80000000u >> lz);
                                 pairs[t++] = ((uint32_t)row << 16) |
-                                             (uint32_t)(a * SL + 32 * w + cnt - 1 - b);
+                                             (uint32_t)(a * SL + 32 * w + cnt - 32 + lz);
                             }
                         }
                     ++st_flag;
                     st_pairs += nc;
                 }
                 __syncwarp();
-                // stage 2: fp32 distances of the warp's pairs, one pair per lane and pass.
-                // (lanes whose flagged neighbours overflowed leave holes; holes are never read.)
+                // stage 2: fp32 distances of the warp's pairs, one pair per lane and pass
+                // (lanes that overflowed leave holes in [0, total); holes are never read back)
                 for (int pi = lane; pi < total; pi += 32) {
                     const uint32_t pr = pairs[pi];
                     const int prow = (int)(pr >> 16) & 127;
@@ -541,15 +603,17 @@ bmu_tc_kernel(const __grid_constant__ CUtensorMap tmX, const TcParams p)
                 __syncwarp();
                 if (flagged) {
                     float best = __int_as_float(0x7f800000);
+#pragma unroll 1
                     for (int t = 0; t < nc; ++t) best = fminf(best, d2buf[pbase + t]);
                     const float bound = best * (1.0f + eps32) + 1.0e-30f;
                     int nsurv = 0, surv0 = -1;
+#pragma unroll 1
                     for (int t = 0; t < nc; ++t)
                         if (d2buf[pbase + t] <= bound) {
                             if (nsurv == 0) surv0 = (int)(pairs[pbase + t] & 0xFFFFu);
                             ++nsurv;
                         }
-                    if (nsurv == 1 && surv0 < pl.K) {
+                    if (nsurv == 1) {
                         label = surv0 + 1;
                     } else if (nsurv >= 2) {
                         // stage 3: fp64 replica of the reference loop over the survivors, in node
@@ -557,6 +621,7 @@ bmu_tc_kernel(const __grid_constant__ CUtensorMap tmX, const TcParams p)
                         ++st_fp64;
                         double bestd = DBL_MAX;
                         int bestk = -1;
+#pragma unroll 1
                         for (int t = 0; t < nc; ++t) {
                             if (!(d2buf[pbase + t] <= bound)) continue;
                             const int k = (int)(pairs[pbase + t] & 0xFFFFu);
@@ -578,9 +643,9 @@ bmu_tc_kernel(const __grid_constant__ CUtensorMap tmX, const TcParams p)
                     ++st_fix;
                     atomicAdd(&p.ctl->fixup_count, 1);
                 }
-                p.labels[p.compact_labels ? j * kTile + row : grow] = label;
+                *lab_ptr = label;
             } else if (p.compact_labels) {
-                p.labels[j * kTile + row] = 0;  // padding row of the last tile: never counted
+                *lab_ptr = 0;  // padding row of the last tile: never counted
             }
             // all reads of this X stage by this warp are done
             __syncwarp();
@@ -594,17 +659,18 @@ bmu_tc_kernel(const __grid_constant__ CUtensorMap tmX, const TcParams p)
         }
 
         if (p.stats) {
+            unsigned long long a = st_flag, b = st_pairs, c = st_fp64, d = st_fix;
             for (int o = 16; o > 0; o >>= 1) {
-                st_flag += __shfl_xor_sync(~0u, st_flag, o);
-                st_pairs += __shfl_xor_sync(~0u, st_pairs, o);
-                st_fp64 += __shfl_xor_sync(~0u, st_fp64, o);
-                st_fix += __shfl_xor_sync(~0u, st_fix, o);
+                a += __shfl_xor_sync(~0u, a, o);
+                b += __shfl_xor_sync(~0u, b, o);
+                c += __shfl_xor_sync(~0u, c, o);
+                d += __shfl_xor_sync(~0u, d, o);
             }
             if (lane == 0) {
-                if (st_flag) atomicAdd(p.stats + PIXIE_STAT_ROWS_FLAGGED, st_flag);
-                if (st_pairs) atomicAdd(p.stats + PIXIE_STAT_PAIRS, st_pairs);
-                if (st_fp64) atomicAdd(p.stats + PIXIE_STAT_ROWS_FP64, st_fp64);
-                if (st_fix) atomicAdd(p.stats + PIXIE_STAT_ROWS_FIXUP, st_fix);
+                if (a) atomicAdd(p.stats + PIXIE_STAT_ROWS_FLAGGED, a);
+                if (b) atomicAdd(p.stats + PIXIE_STAT_PAIRS, b);
+                if (c) atomicAdd(p.stats + PIXIE_STAT_ROWS_FP64, c);
+                if (d) atomicAdd(p.stats + PIXIE_STAT_ROWS_FIXUP, d);
             }
         }
     }
@@ -643,17 +709,21 @@ cudaError_t launch_bmu_tc(const CUtensorMap &tmX, const TcParams &p, int num_sms
     PIXIE_VARIANT(32, 1, 1, 4)
     PIXIE_VARIANT(32, 2, 1, 4)
     PIXIE_VARIANT(48, 2, 1, 4)
+    PIXIE_VARIANT(50, 2, 1, 4)
     PIXIE_VARIANT(56, 2, 1, 4)
     PIXIE_VARIANT(64, 2, 1, 4)
     PIXIE_VARIANT(32, 1, 1, 2)
     PIXIE_VARIANT(32, 2, 1, 2)
     PIXIE_VARIANT(48, 2, 1, 2)
+    PIXIE_VARIANT(50, 2, 1, 2)
     PIXIE_VARIANT(56, 2, 1, 2)
     PIXIE_VARIANT(64, 2, 1, 2)
     PIXIE_VARIANT(80, 2, 1, 2)
+    PIXIE_VARIANT(100, 2, 1, 2)
     PIXIE_VARIANT(104, 2, 1, 2)
     PIXIE_VARIANT(128, 2, 1, 2)
     PIXIE_VARIANT(80, 2, 2, 2)
+    PIXIE_VARIANT(100, 2, 2, 2)
     PIXIE_VARIANT(104, 2, 2, 2)
     PIXIE_VARIANT(128, 2, 2, 2)
 #undef PIXIE_VARIANT

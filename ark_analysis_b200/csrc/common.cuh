@@ -12,8 +12,8 @@ namespace pixie {
 
 constexpr int kTile = PIXIE_TILE;  // rows per tile == UMMA M == TMEM lanes
 constexpr int kLabelFixup = -1;    // sentinel: row must be resolved by the exact fix-up kernel
-constexpr int kMaxCand = 16;       // candidate nodes kept per row before giving up to the fix-up
-constexpr int kWarpPairCap = 128;  // (row, node) pairs re-evaluated per tile by one epilogue warp
+constexpr int kMaxCand = 15;       // candidate nodes kept per row before giving up to the fix-up
+constexpr int kWarpPairCap = 256;  // (row, node) pairs re-evaluated per tile by one epilogue warp
 constexpr int kMaxStages = 8;
 
 // Device-side result of the codebook preparation kernel, read by the BMU kernel.
@@ -21,7 +21,7 @@ struct CodebookAux {
     int wmax_bits;  // float bits of max_k ||w_k|| (atomicMax on the non-negative float pattern)
     int nonfinite;
     int fixup_count;  // rows the tensor-core kernel handed to the exact fix-up kernel
-    int pad;
+    int w_has_negative;  // any codebook entry with the sign bit set (disables the one-sided bound)
 };
 
 // Host-side plan of the tensor-core BMU kernel for one (C, K).
@@ -36,8 +36,9 @@ struct TcPlan {
     int spc;     // slices per accumulator chunk               (template parameter)
     int NCH;     // accumulator chunks per tile, 1 or 2        (template parameter)
     int NG;      // epilogue groups of 4 warps, 2 or 4         (template parameter)
-    int Nmma;    // UMMA N = SL * spc (multiple of 16, <= 256)
-    int Ntot;    // NCH * Nmma >= K: codebook rows in the image (padded rows never win)
+    int Nchunk;  // codebook rows covered by one accumulator chunk = SL * spc
+    int Nmma;    // UMMA N = Nchunk rounded up to 16 (<= 256); columns past Nchunk are never read
+    int Ntot;    // codebook rows in the image = (NCH - 1) * Nchunk + Nmma (rows >= K never win)
     int nbuf;    // TMEM accumulator buffers: NG when NCH == 1, else 2
     int tmem_cols;
     int nstage;  // X tile pipeline depth (multiple of NG)

@@ -49,6 +49,8 @@ __device__ __forceinline__ void mbar_arrive_expect_tx(uint32_t bar, uint32_t byt
 __device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity)
 {
     uint32_t ok;
+    // no suspend-time hint: with a hint ptxas emits TRYWAIT + NANOSLEEP and the wake-up after the
+    // phase completes is slow enough to cost 40 % of the kernel (measured, profiles/r01_notes.md)
     asm volatile(
         "{\n\t.reg .pred P;\n\t"
         "mbarrier.try_wait.parity.shared::cta.b64 P, [%1], %2;\n\t"
@@ -58,12 +60,24 @@ __device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity)
         : "memory");
     return ok != 0;
 }
-// Bounded spin: a wedged pipeline traps (-> cudaErrorLaunchFailure) instead of hanging the GPU.
+__device__ __forceinline__ uint64_t global_timer_ns()
+{
+    uint64_t t;
+    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+    return t;
+}
+// Bounded wait: a wedged pipeline traps (-> cudaErrorLaunchFailure) after ~2 s instead of hanging
+// the GPU.  The clock is only read every 4096 failed probes, i.e. never on the normal path.
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity)
 {
     uint32_t spins = 0;
+    uint64_t t0 = 0;
     while (!mbar_try_wait(bar, parity)) {
-        if (++spins > (1u << 26)) __trap();
+        if ((++spins & 4095u) == 0u) {
+            const uint64_t now = global_timer_ns();
+            if (t0 == 0) t0 = now;
+            if (now - t0 > 2000000000ull) __trap();
+        }
     }
 }
 
@@ -159,6 +173,20 @@ __device__ __forceinline__ void mma_commit(uint32_t bar)
 #define PIXIE_R16(v, o) PIXIE_R8(v, o), PIXIE_R8(v, o + 8)
 #define PIXIE_R32(v, o) PIXIE_R16(v, o), PIXIE_R16(v, o + 16)
 
+__device__ __forceinline__ void tmem_ld2(uint32_t taddr, uint32_t *v)
+{
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x2.b32 {%0, %1}, [%2];"
+                 : "=r"(v[0]), "=r"(v[1])
+                 : "r"(taddr)
+                 : "memory");
+}
+__device__ __forceinline__ void tmem_ld4(uint32_t taddr, uint32_t *v)
+{
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x4.b32 {%0, %1, %2, %3}, [%4];"
+                 : PIXIE_R4(v, 0)
+                 : "r"(taddr)
+                 : "memory");
+}
 __device__ __forceinline__ void tmem_ld8(uint32_t taddr, uint32_t *v)
 {
     asm volatile(
@@ -199,11 +227,11 @@ __device__ __forceinline__ void tmem_ld64(uint32_t taddr, uint32_t *v)
         : "memory");
 }
 
-// Loads N (multiple of 8, <= 128) consecutive columns with the fewest instructions.
+// Loads N (even, <= 128) consecutive columns with the fewest instructions.
 template <int N>
 __device__ __forceinline__ void tmem_ld_cols(uint32_t taddr, uint32_t *v)
 {
-    static_assert(N % 8 == 0 && N >= 8 && N <= 128, "slice width");
+    static_assert(N % 2 == 0 && N >= 2 && N <= 128, "slice width");
     int o = 0;
     if constexpr (N >= 64) {
         tmem_ld64(taddr, v);
@@ -226,6 +254,58 @@ __device__ __forceinline__ void tmem_ld_cols(uint32_t taddr, uint32_t *v)
         tmem_ld8(taddr + o, v + o);
         o += 8;
     }
+    if constexpr ((R % 8) >= 4) {
+        tmem_ld4(taddr + o, v + o);
+        o += 4;
+    }
+    if constexpr ((R % 4) >= 2) {
+        tmem_ld2(taddr + o, v + o);
+        o += 2;
+    }
+}
+
+// 128-bit shared-memory load from a 32-bit shared address
+__device__ __forceinline__ uint4 lds128(uint32_t addr)
+{
+    uint4 r;
+    asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];"
+                 : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w)
+                 : "r"(addr));
+    return r;
+}
+
+// ---------------------------------------------------------------- packed fp32 (FADD2 / FFMA2)
+__device__ __forceinline__ uint64_t pack2(float lo, float hi)
+{
+    uint64_t r;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+    return r;
+}
+__device__ __forceinline__ uint64_t pack2u(uint32_t lo, uint32_t hi)
+{
+    uint64_t r;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "r"(lo), "r"(hi));
+    return r;
+}
+__device__ __forceinline__ void unpack2u(uint64_t v, uint32_t &lo, uint32_t &hi)
+{
+    asm("mov.b64 {%0, %1}, %2;" : "=r"(lo), "=r"(hi) : "l"(v));
+}
+__device__ __forceinline__ void unpack2(uint64_t v, float &lo, float &hi)
+{
+    asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v));
+}
+__device__ __forceinline__ uint64_t sub2(uint64_t a, uint64_t b)
+{
+    uint64_t r;
+    asm("sub.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+    return r;
+}
+__device__ __forceinline__ uint64_t fma2(uint64_t a, uint64_t b, uint64_t c)
+{
+    uint64_t r;
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c));
+    return r;
 }
 
 // ---------------------------------------------------------------- descriptors
