@@ -225,6 +225,17 @@ int pixie_bmu_dist_f64(const float *X, int64_t n, int32_t C, int64_t ldX, const 
     return PIXIE_OK;
 }
 
+int pixie_cluster_sums_f32(const float *X, int64_t n, int32_t C, int64_t ldX, const int32_t *labels,
+                           int32_t K, double *SN, void *workspace, size_t ws_bytes, void *stream)
+{
+    if (bad_shape(n, C, ldX, K) || !labels || !SN || (n > 0 && !X)) return PIXIE_ERR_INVALID_ARG;
+    Workspace ws = carve(workspace, 0, C, K);
+    if (!workspace || ws_bytes < ws.total) return PIXIE_ERR_WORKSPACE;
+    PX_CUDA(launch_cluster_sums(X, n, C, ldX, labels, 0, K, 0, 1, (n + kTile - 1) / kTile,
+                                ws.partials, kSumParts, SN, reinterpret_cast<cudaStream_t>(stream)));
+    return PIXIE_OK;
+}
+
 int pixie_som_accum_f32(const float *X, int64_t n, int32_t C, int64_t ldX, const float *W32,
                         int32_t K, int64_t tile_first, int64_t tile_stride, double *SN,
                         void *workspace, size_t ws_bytes, uint32_t flags,

@@ -16,7 +16,7 @@ from ._native import (FLAG_AUTO, FLAG_FORCE_EXACT, FLAG_FORCE_TC, NSTATS, TILE, 
                       PixieError)
 
 __all__ = [
-    "to_device_matrix", "bmu", "bmu_dists", "cluster_sums", "som_accum", "som_apply", "train_som",
+    "to_device_matrix", "bmu", "bmu_dists", "cluster_sums", "label_sums", "som_accum", "som_apply", "train_som",
     "som", "map_data_to_nodes", "default_radius", "init_codebook_indices", "default_batches",
     "grid_chebyshev",
 ]
@@ -170,6 +170,24 @@ def cluster_sums(X, W, labels=None):
     return bmu(X, W, labels=labels, want_sums=True)
 
 
+def label_sums(X, labels, K):
+    """Per-cluster channel sums and counts SN [K, C+1] (float64) for an existing int32 label
+    tensor with values in 1..K (the aggregate of pixel_cluster_utils.py:369-374)."""
+    n, C, ld = _check_x(X)
+    dev = X.device
+    _require_cuda(labels, "labels")
+    if labels.dtype != torch.int32 or labels.numel() != n or not labels.is_contiguous():
+        raise PixieError("labels must be a contiguous int32 tensor of length n")
+    SN = torch.zeros((K, C + 1), dtype=torch.float64, device=dev)
+    if n:
+        with torch.cuda.device(dev):
+            ws = _workspace(0, C, K, dev)
+            rc = _native.lib().pixie_cluster_sums_f32(_ptr(X), n, C, ld, _ptr(labels), int(K),
+                                                      _ptr(SN), _ptr(ws), ws.numel(), _stream(dev))
+        _native.check(rc, "pixie_cluster_sums_f32")
+    return SN
+
+
 def som_accum(X, W32, tile_first, tile_stride, SN=None, flags=FLAG_AUTO, stats=None):
     """One mini-batch of the batch SOM: BMU of the rows of tiles tile_first, tile_first+stride, ...
     against W32 and their per-node sums/counts SN [K, C+1] float64."""
@@ -198,13 +216,7 @@ def som_apply(W64, W32, SN, xdim, ydim, sigma, alpha):
     _native.check(rc, "pixie_som_apply_f64")
 
 
-def step_schedule(t, T, alpha_range, radius_range):
-    """(sigma, alpha) of step t of T."""
-    frac = t / T
-    r = radius_range[0] - (radius_range[0] - radius_range[1]) * frac
-    r_eff = 0.5 if r < 1.0 else r
-    alpha = alpha_range[0] - (alpha_range[0] - alpha_range[1]) * frac
-    return 0.5 * r_eff, alpha
+from .distributed import run_training_steps, step_schedule  # noqa: E402,F401
 
 
 def train_som(X, W0, xdim, ydim, rlen=1, alpha_range=(0.05, 0.01), radius_range=None,
@@ -245,15 +257,12 @@ def train_som(X, W0, xdim, ydim, rlen=1, alpha_range=(0.05, 0.01), radius_range=
         _native.check(rc, "pixie_som_train_f32")
         return W64
     import torch.distributed as dist
-    T = int(rlen) * B
     som_apply(W64, W32, SN, xdim, ydim, 1.0, 0.0)  # W32 = fp32(W64)
-    for t in range(T):
-        m = t % B
-        first = (m - tile_offset) % B  # local tiles whose GLOBAL index is congruent to m mod B
-        som_accum(X, W32, first, B, SN=SN, flags=flags)
-        dist.all_reduce(SN, op=dist.ReduceOp.SUM, group=group)
-        sigma, alpha = step_schedule(t, T, alpha_range, radius_range)
-        som_apply(W64, W32, SN, xdim, ydim, sigma, alpha)
+    run_training_steps(
+        rlen, B, int(tile_offset), alpha_range, radius_range,
+        accum=lambda first, stride: som_accum(X, W32, first, stride, SN=SN, flags=flags),
+        allreduce=lambda stats: dist.all_reduce(stats, op=dist.ReduceOp.SUM, group=group),
+        apply=lambda stats, sigma, alpha: som_apply(W64, W32, stats, xdim, ydim, sigma, alpha))
     return W64
 
 
@@ -288,7 +297,7 @@ def som(data, xdim=10, ydim=10, rlen=10, alpha_range=(0.05, 0.01), radius_range=
     return W.cpu().numpy()
 
 
-def map_data_to_nodes(nodes, newdata, device=None, chunk_rows=1 << 20):
+def map_data_to_nodes(nodes, newdata, device=None, chunk_rows=1 << 20, return_dists=True):
     """Drop-in for ``pyFlowSOM.map_data_to_nodes`` (cluster_helpers.py:152-157): returns
     ``(labels int32 1-indexed, dists float64)`` for host arrays, through the host-buffer C entry
     point (pinned-or-pageable host memory in, chunked H2D / kernel / D2H overlap)."""
@@ -300,7 +309,7 @@ def map_data_to_nodes(nodes, newdata, device=None, chunk_rows=1 << 20):
     m, C = newdata.shape
     K = nodes.shape[0]
     labels = np.empty(m, np.int32)
-    dists = np.empty(m, np.float64)
+    dists = np.empty(m, np.float64) if return_dists else None
     if m == 0:
         return labels, dists
     L = _native.lib()
@@ -311,7 +320,8 @@ def map_data_to_nodes(nodes, newdata, device=None, chunk_rows=1 << 20):
         newdata = newdata.astype(np.float64, copy=False)
         fn = L.pixie_map_data_to_nodes_host_f64
     rc = fn(nodes.ctypes.data_as(ctypes.c_void_p), K, newdata.ctypes.data_as(ctypes.c_void_p), m, C,
-            labels.ctypes.data_as(ctypes.c_void_p), dists.ctypes.data_as(ctypes.c_void_p),
+            labels.ctypes.data_as(ctypes.c_void_p),
+            dists.ctypes.data_as(ctypes.c_void_p) if return_dists else None,
             device.index if device.index is not None else -1, int(chunk_rows))
     _native.check(rc, "pixie_map_data_to_nodes_host")
     return labels, dists

@@ -79,6 +79,15 @@ int pixie_bmu_dist_f64(const float *X, int64_t n, int32_t C, int64_t ldX, const 
                        const int32_t *labels, double *dists, void *stream);
 
 /*
+ * Per-node channel sums and counts for an EXISTING label array (labels 1..K; anything else is
+ * skipped): SN = double[K x (C+1)], row k = [sum of X rows labelled k+1 | their count].  This is
+ * the per-FOV aggregate of compute_pixel_cluster_channel_avg (pixel_cluster_utils.py:369-374:
+ * groupby(cluster)[channels].sum() and .size()).  Deterministic (fixed summation order).
+ */
+int pixie_cluster_sums_f32(const float *X, int64_t n, int32_t C, int64_t ldX, const int32_t *labels,
+                           int32_t K, double *SN, void *workspace, size_t ws_bytes, void *stream);
+
+/*
  * One mini-batch step of the batch SOM (the B200 replacement for pyFlowSOM.som's inner loop,
  * cluster_helpers.py:106-109; algorithm in DESIGN.md section 4).  Visits tiles
  * tile_first, tile_first + tile_stride, ... (< ceil(n / PIXIE_TILE)), finds each row's BMU against
