@@ -20,7 +20,7 @@ STAT_ROWS_FLAGGED, STAT_PAIRS, STAT_ROWS_FP64, STAT_ROWS_FIXUP, STAT_KERNEL = 0,
 
 # every symbol include/pixie_b200.h declares (checked by tests/test_capi_symbols.py)
 SYMBOLS = [
-    "pixie_version", "pixie_error_string", "pixie_device_count", "pixie_workspace_bytes",
+    "pixie_version", "pixie_error_string", "pixie_kernel_launches", "pixie_device_count", "pixie_workspace_bytes",
     "pixie_bmu_f32", "pixie_bmu_dist_f64", "pixie_cluster_sums_f32", "pixie_som_accum_f32", "pixie_som_apply_f64",
     "pixie_som_train_f32", "pixie_map_data_to_nodes_host_f32", "pixie_map_data_to_nodes_host_f64",
 ]
@@ -71,6 +71,7 @@ def lib():
         L.pixie_error_string.restype = c.c_char_p
         L.pixie_error_string.argtypes = [c.c_int]
         L.pixie_device_count.restype = c.c_int
+        L.pixie_kernel_launches.restype = c.c_ulonglong
         L.pixie_workspace_bytes.restype = sz
         L.pixie_workspace_bytes.argtypes = [i64, i32, i32]
         L.pixie_bmu_f32.argtypes = [vp, i64, i32, i64, vp, i32, vp, vp, vp, sz, u32, vp, vp]

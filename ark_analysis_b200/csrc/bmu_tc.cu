@@ -174,6 +174,7 @@ cudaError_t launch_codebook_prep(const float *W, int K, int C, const TcPlan &pla
     const int rows_per_block = 8;
     codebook_prep_kernel<<<(plan.Ntot + rows_per_block - 1) / rows_per_block, 256, 0, stream>>>(
         W, K, C, plan.C8, plan.nblkW, plan.Ntot, wimg, aux);
+    count_launch();
     return cudaGetLastError();
 }
 
@@ -693,6 +694,7 @@ static cudaError_t launch_one(const CUtensorMap &tmX, const TcParams &p, int gri
                                          (int)p.plan.smem_bytes);
     if (e != cudaSuccess) return e;
     bmu_tc_kernel<SL, SPC, NCH, NG><<<grid, NG * 128 + 64, p.plan.smem_bytes, stream>>>(tmX, p);
+    count_launch();
     return cudaGetLastError();
 }
 

@@ -3,12 +3,18 @@
 #include <stdio.h>
 #include <string.h>
 
+#include <atomic>
 #include <mutex>
 #include <vector>
 
 #include "common.cuh"
 
 using namespace pixie;
+
+namespace pixie {
+static std::atomic<unsigned long long> g_launches{0};
+void count_launch(int n) { g_launches.fetch_add((unsigned long long)n, std::memory_order_relaxed); }
+}  // namespace pixie
 
 namespace {
 
@@ -133,6 +139,7 @@ int bmu_tiles(const float *X, int64_t n, int C, int64_t ldX, const float *W, int
                                  compact, nullptr, stream));
         if (stats) {
             set_u64_kernel<<<1, 1, 0, stream>>>(stats + PIXIE_STAT_KERNEL, 2ull);
+            count_launch();
         }
         return PIXIE_OK;
     }
@@ -156,6 +163,7 @@ int bmu_tiles(const float *X, int64_t n, int C, int64_t ldX, const float *W, int
                              &ws.aux->fixup_count, stream));
     if (stats) {
         set_u64_kernel<<<1, 1, 0, stream>>>(stats + PIXIE_STAT_KERNEL, 1ull);
+        count_launch();
     }
     return PIXIE_OK;
 }
@@ -182,6 +190,11 @@ const char *pixie_error_string(int code)
         case PIXIE_ERR_NO_DEVICE: return "no CUDA device";
         default: return "unknown error";
     }
+}
+
+unsigned long long pixie_kernel_launches(void)
+{
+    return pixie::g_launches.load(std::memory_order_relaxed);
 }
 
 int pixie_device_count(void)
@@ -409,6 +422,7 @@ int map_data_host(const TIn *nodes, int32_t K, const TIn *data, int64_t n, int32
         PX_CUDA(cudaMemcpyAsync(ctx->dW64, nodes, (size_t)K * C * sizeof(double),
                                 cudaMemcpyHostToDevice, s0));
         f64_to_f32_kernel<<<64, 256, 0, s0>>>(ctx->dW64, ctx->dW, (int64_t)K, C, (int64_t)C);
+        count_launch();
     } else {
         PX_CUDA(cudaMemcpyAsync(ctx->dW, nodes, (size_t)K * C * sizeof(float),
                                 cudaMemcpyHostToDevice, s0));
@@ -428,6 +442,7 @@ int map_data_host(const TIn *nodes, int32_t K, const TIn *data, int64_t n, int32
                                     (size_t)rows * C * sizeof(double), cudaMemcpyHostToDevice, st));
             f64_to_f32_kernel<<<148 * 8, 256, 0, st>>>(
                 reinterpret_cast<const double *>(ctx->dX64[s]), dX, rows, C, ld);
+            count_launch();
         } else if (ld == C) {
             PX_CUDA(cudaMemcpyAsync(dX, data + (size_t)r0 * C, (size_t)rows * C * sizeof(float),
                                     cudaMemcpyHostToDevice, st));

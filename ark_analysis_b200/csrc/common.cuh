@@ -80,6 +80,9 @@ cudaError_t launch_cluster_sums(const float *X, int64_t n, int C, int64_t ldX,
 cudaError_t launch_som_apply(double *W64, float *W32, const double *SN, int xdim, int ydim, int C,
                              double sigma, double alpha, cudaStream_t stream);
 
+// process-wide count of kernels this library has launched (pixie_kernel_launches())
+void count_launch(int n = 1);
+
 // number of per-CTA partial buffers the cluster-sums kernel uses
 constexpr int kSumParts = 148;
 

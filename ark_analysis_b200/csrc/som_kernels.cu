@@ -60,6 +60,7 @@ cudaError_t launch_bmu_exact(const float *X, int64_t n, int C, int64_t ldX, cons
     bmu_exact_kernel<<<(unsigned)grid, 128, 0, stream>>>(X, n, C, ldX, W, K, labels, tile_first,
                                                         tile_stride, ntiles, compact_labels,
                                                         fixup_count_or_null);
+    count_launch();
     return cudaGetLastError();
 }
 
@@ -93,6 +94,7 @@ cudaError_t launch_bmu_dist(const float *X, int64_t n, int C, int64_t ldX, const
     int64_t blocks = (n + 255) / 256;
     if (blocks > 148 * 32) blocks = 148 * 32;
     bmu_dist_kernel<<<(unsigned)blocks, 256, 0, stream>>>(X, n, C, ldX, W, K, labels, dists);
+    count_launch();
     return cudaGetLastError();
 }
 
@@ -219,9 +221,11 @@ cudaError_t launch_cluster_sums(const float *X, int64_t n, int C, int64_t ldX,
     cluster_sums_kernel<<<nparts, kSumThreads, smem, stream>>>(X, n, C, ldX, labels,
                                                               compact_labels, K, tile_first,
                                                               tile_stride, ntiles, partials);
+    count_launch();
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return e;
     reduce_partials_kernel<<<(len + 255) / 256, 256, 0, stream>>>(partials, nparts, len, SN);
+    count_launch();
     return cudaGetLastError();
 }
 
@@ -274,6 +278,7 @@ cudaError_t launch_som_apply(double *W64, float *W32, const double *SN, int xdim
 {
     const double inv2s2 = 1.0 / (2.0 * sigma * sigma);
     som_apply_kernel<<<xdim * ydim, 128, 0, stream>>>(W64, W32, SN, xdim, ydim, C, inv2s2, alpha);
+    count_launch();
     return cudaGetLastError();
 }
 

@@ -1,0 +1,412 @@
+#!/usr/bin/env python
+"""bench.py -- Pixie SOM throughput on B200 (BASELINE.json metric), one JSON line on rank 0.
+
+    python bench.py --gpus 1 --steps K --warmup W
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
+    python bench.py --impl reference ...      # the reference's CPU path on the host cores
+
+Workload (config.workload): BASELINE.json configs[1] per GPU -- 50 synthetic 1024 x 1024 FOVs x 32
+channels, 10 x 10 SOM.  A STEP is one pass of the hot path over that data:
+  (1) train   -- one training pass (num_passes=1, 32 mini-batches: BMU + per-node aggregation +
+                 codebook update) over the 10 % pixel subset (5,242,880 rows per GPU); with N > 1
+                 one NCCL all-reduce of the K x (C+1) statistics per mini-batch;
+  (2) assign  -- BMU label of every pixel (52,428,800 rows per GPU) against the trained codebook.
+`value` = pixels visited per second (train rows + assign rows, all GPUs) with the data resident in
+HBM; `e2e` = the same step through the host-buffer API (pinned host memory in, labels out).
+Weak scaling: every rank owns its own 50 FOVs.  Inputs (6.7 GB per GPU) are far larger than L2.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "pixie_som_pixels_per_s"
+UNIT = "pixels/s"
+NFOV, HW, C, XD, YD = 50, 1024, 32, 10, 10
+K = XD * YD
+BATCHES = 32
+SUBSET = 0.1
+SEED = 42
+
+
+def measured_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return float(d["hbm_gbs"]), "measured (MEASURED_PEAKS.json, copy bandwidth)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+def workload_config(n_gpus):
+    return {
+        "workload": f"Pixie pixel SOM: {NFOV} synthetic {HW}x{HW} FOVs x {C} channels per GPU, "
+                    f"{XD}x{YD} SOM (BASELINE.json configs[1]); step = 1 training pass over the "
+                    f"10% subset ({BATCHES} mini-batches) + BMU assignment of every pixel",
+        "fovs_per_gpu": NFOV, "fov_shape": [HW, HW], "channels": C, "som": [XD, YD],
+        "assign_rows_per_gpu": NFOV * HW * HW,
+        "train_rows_per_gpu": NFOV * (int(HW * HW * SUBSET) // 128 * 128),
+        "batches_per_pass": BATCHES, "num_passes": 1, "distribution": "pixie-like (P)",
+        "parallelism": f"fov-sharded x{n_gpus}" if n_gpus > 1 else "single gpu",
+        "l2": "inputs (6.7 GB/GPU) larger than L2; no flush needed",
+    }
+
+
+# ------------------------------------------------------------------------------------------------
+# synthetic data (distribution "P")
+# ------------------------------------------------------------------------------------------------
+def prototypes():
+    r = np.random.default_rng(12345)
+    return r.dirichlet(np.full(C, 0.3), size=30).astype(np.float32)
+
+
+def gen_fovs_device(torch, device, fov_ids, out):
+    """Fill `out` [len(fov_ids) * HW*HW, C] with Pixie-like rows, FOV f seeded 42 + f."""
+    protos = torch.from_numpy(prototypes()).to(device)
+    npx = HW * HW
+    norm = None
+    for i, f in enumerate(fov_ids):
+        g = torch.Generator(device=device).manual_seed(SEED + int(f))
+        which = torch.randint(0, protos.shape[0], (npx,), device=device, generator=g)
+        x = protos[which]
+        x += torch.randn((npx, C), device=device, generator=g).abs_() * 0.05
+        x /= x.sum(1, keepdim=True)
+        if norm is None:
+            # per-channel 99.9th percentile, estimated on the first FOV (Pixie's channel norm)
+            norm = torch.stack([x[:, c].kthvalue(int(0.999 * npx)).values for c in range(C)])
+        x /= norm
+        out[i * npx:(i + 1) * npx] = x
+        del x, which
+    return out
+
+
+def gen_fovs_host(fov_ids):
+    """numpy twin of gen_fovs_device for the CPU arm (distribution only; values differ)."""
+    r = np.random.default_rng(SEED)
+    protos = prototypes()
+    npx = HW * HW
+    out = np.empty((len(fov_ids) * npx, C), np.float32)
+    for i, _ in enumerate(fov_ids):
+        x = protos[r.integers(0, 30, npx)] + np.abs(r.normal(0, 0.05, (npx, C))).astype(np.float32)
+        x /= x.sum(1, keepdims=True)
+        out[i * npx:(i + 1) * npx] = x
+    out /= np.quantile(out[:npx], 0.999, axis=0)
+    return out
+
+
+# ------------------------------------------------------------------------------------------------
+# clocks sampler (nvidia-smi during the timed region)
+# ------------------------------------------------------------------------------------------------
+class ClockSampler:
+    FIELDS = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,"
+              "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+              "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index = index
+        self.samples = []
+        self.proc = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.FIELDS}",
+                 "--format=csv,noheader,nounits", "-lms", "100"],
+                stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except OSError:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            parts = [p.strip() for p in line.split(",")]
+            if len(parts) >= 6:
+                self.samples.append(parts)
+
+    def stop(self):
+        if self.proc is not None:
+            self.proc.terminate()
+        sm = [float(s[0]) for s in self.samples if s[0].replace(".", "").isdigit()]
+        mx = [float(s[1]) for s in self.samples if s[1].replace(".", "").isdigit()]
+        reasons = []
+        for name, col in (("hw_slowdown", 2), ("hw_thermal_slowdown", 3),
+                          ("sw_thermal_slowdown", 4), ("sw_power_cap", 5)):
+            if any(s[col].lower().startswith("active") for s in self.samples):
+                reasons.append(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None,
+                "sm_max_mhz": max(mx) if mx else None, "reasons": reasons,
+                "samples": len(self.samples)}
+
+
+# ------------------------------------------------------------------------------------------------
+# CPU arm: the reference's path restated (oracle), on the host cores
+# ------------------------------------------------------------------------------------------------
+def cpu_sample_run(X, cores):
+    """One bounded sample of the step on the CPU: online SOM pass over the 10 % subset (the
+    reference's training rule, sequential) + map_data_to_nodes over every row in 1e6-row chunks
+    (cluster_helpers.py:150-157), row ranges spread over `cores` threads like the reference's
+    FOV-level process pool.  Returns (pixels, seconds, train_seconds, assign_seconds)."""
+    import oracle
+    n = X.shape[0]
+    ntrain = int(n * SUBSET)
+    r = np.random.default_rng(SEED)
+    train = np.ascontiguousarray(X[r.choice(n, ntrain, replace=False)], np.float64)
+    t0 = time.perf_counter()
+    W = oracle.som_online(train, XD, YD, rlen=1, alpha_range=(0.05, 0.01), seed=SEED)
+    t1 = time.perf_counter()
+    for lo in range(0, n, 1_000_000):
+        chunk = np.ascontiguousarray(X[lo:lo + 1_000_000], np.float64)  # the reference's f64 copy
+        oracle.map_data_to_nodes_mt(W, chunk, cores)
+    t2 = time.perf_counter()
+    return n + ntrain, t2 - t0, t1 - t0, t2 - t1
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    import oracle
+    oracle.build()
+    cores = len(os.sched_getaffinity(0))
+    rows = 2 * HW * HW  # bounded sample: 2 of the 50 FOVs per step
+    X = gen_fovs_host([0, 1])
+    for _ in range(args.warmup if args.warmup < 2 else 1):
+        cpu_sample_run(X[:HW * HW // 4], cores)
+    tot_px, tot_s, tr_s, as_s = 0, 0.0, 0.0, 0.0
+    for _ in range(args.steps):
+        px, s, tr, a = cpu_sample_run(X, cores)
+        tot_px += px
+        tot_s += s
+        tr_s += tr
+        as_s += a
+    value = tot_px / tot_s
+    sample = (f"{rows} rows (2 of {NFOV} FOVs) per step: online SOM pass over the 10% subset "
+              f"(1 thread, sequential rule) + map_data_to_nodes over all rows in 1e6-row chunks "
+              f"on {cores} threads; oracle/pixie_oracle.c, gcc -O2")
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * tot_s / args.steps,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
+        "data": "synthetic", "config": workload_config(args.gpus),
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port",
+                         "sample": sample,
+                         "train_pixels_per_s": int(rows * SUBSET) * args.steps / tr_s,
+                         "assign_pixels_per_s": rows * args.steps / as_s},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------------------------
+# GPU arm
+# ------------------------------------------------------------------------------------------------
+def run_gpu(args):
+    import torch
+    import torch.distributed as dist
+
+    from ark_analysis_b200 import _native
+    from ark_analysis_b200 import som as S
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device (no CPU fallback); use --impl reference "
+                         "for the CPU arm")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    distributed = world > 1
+    if distributed:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+    lib = _native.lib()
+
+    # ---- resident synthetic data: this rank's 50 FOVs and their 10 % training subset
+    npx = HW * HW
+    n = NFOV * npx
+    fov_ids = list(range(rank * NFOV, (rank + 1) * NFOV))
+    X = torch.empty((n, C), dtype=torch.float32, device=dev)
+    gen_fovs_device(torch, dev, fov_ids, X)
+    ntrain_fov = int(npx * SUBSET) // 128 * 128  # tile aligned per FOV (104,832 of 104,857 rows)
+    g = torch.Generator(device=dev).manual_seed(SEED + 1000 + rank)
+    Xt = torch.empty((NFOV * ntrain_fov, C), dtype=torch.float32, device=dev)
+    for i in range(NFOV):
+        idx = torch.randperm(npx, device=dev, generator=g)[:ntrain_fov]
+        Xt[i * ntrain_fov:(i + 1) * ntrain_fov] = X[i * npx:(i + 1) * npx][idx]
+    ntrain = Xt.shape[0]
+    tile_offset = rank * (ntrain // 128)
+    # initial codebook: seeded rows of rank 0's subset, identical on every rank
+    init_idx = S.init_codebook_indices(ntrain, K, SEED)
+    W0 = Xt[torch.as_tensor(init_idx, device=dev)].to(torch.float64)
+    if distributed:
+        dist.broadcast(W0, src=0)
+    labels = torch.empty(n, dtype=torch.int32, device=dev)
+    stats = torch.zeros(S.NSTATS, dtype=torch.int64, device=dev)
+    group = dist.group.WORLD if distributed else None
+
+    def step(ev=None):
+        if ev:
+            ev[0].record()
+        W = S.train_som(Xt, W0, XD, YD, rlen=1, alpha_range=(0.05, 0.01),
+                        batches_per_pass=BATCHES, group=group, tile_offset=tile_offset)
+        W32 = W.to(torch.float32)
+        if ev:
+            ev[1].record()
+        S.bmu(X, W32, labels=labels)
+        if ev:
+            ev[2].record()
+        return W32
+
+    for _ in range(max(args.warmup, 3)):
+        W32 = step()
+    torch.cuda.synchronize()
+    # parity guard inside the bench: a window of the labels against the exact fp64 kernel
+    chk = S.bmu(X[:262144], W32, flags=S.FLAG_FORCE_EXACT)
+    assert torch.equal(chk, labels[:262144]), "bench labels differ from the exact kernel"
+    S.bmu(X, W32, labels=labels, stats=stats)
+    torch.cuda.synchronize()
+    flagged_frac = float(stats[_native.STAT_ROWS_FLAGGED]) / n
+
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    if distributed:
+        dist.barrier()
+    torch.cuda.synchronize()
+    launches0 = lib.pixie_kernel_launches()
+    evs = [[torch.cuda.Event(enable_timing=True) for _ in range(3)] for _ in range(args.steps)]
+    t_wall0 = time.perf_counter()
+    for k in range(args.steps):
+        step(evs[k])
+    end = torch.cuda.Event(enable_timing=True)
+    end.record()
+    torch.cuda.synchronize()
+    if distributed:
+        dist.barrier()
+    wall_ms = 1e3 * (time.perf_counter() - t_wall0)
+    launches = lib.pixie_kernel_launches() - launches0
+    clocks = sampler.stop() if rank == 0 else None
+    total_ms = evs[0][0].elapsed_time(end)
+    train_ms = sum(e[0].elapsed_time(e[1]) for e in evs)
+    assign_ms = sum(e[1].elapsed_time(e[2]) for e in evs)
+    t = torch.tensor([total_ms, train_ms, assign_ms, wall_ms], dtype=torch.float64, device=dev)
+    if distributed:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    total_ms, train_ms, assign_ms, wall_ms = [float(v) for v in t.tolist()]
+    px_step = (n + ntrain) * world
+    value = px_step * args.steps / (total_ms * 1e-3)
+
+    # ---- roofline of the dominant kernel (BMU assignment): algorithmic bytes / measured time
+    peak, peak_src = measured_peaks()
+    assign_ms_launch = assign_ms / args.steps
+    bytes_launch = n * (4 * C + 4)
+    achieved = bytes_launch / (assign_ms_launch * 1e-3) / 1e9
+    traffic = None
+    tp = os.path.join(ROOT, "profiles", "r01_assign_traffic.json")
+    if os.path.exists(tp):
+        traffic = json.load(open(tp)).get("dram_bytes_per_launch")
+    roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
+                "frac": achieved / peak, "traffic": traffic, "kernel": "bmu_tc_kernel (assign)",
+                "bytes_per_pixel": 4 * C + 4, "pixels_per_launch": n, "peak_source": peak_src,
+                "ms_per_launch": assign_ms_launch}
+
+    # ---- e2e: the same step through the host-buffer API (pinned host memory in, labels out)
+    e2e = None
+    if not args.no_e2e:
+        hX = torch.empty((n, C), dtype=torch.float32).pin_memory()
+        hX.copy_(X)
+        hXt = torch.empty((ntrain, C), dtype=torch.float32).pin_memory()
+        hXt.copy_(Xt)
+        hlab = torch.empty(n, dtype=torch.int32).pin_memory()
+        hXn, hXtn, hlabn = hX.numpy(), hXt.numpy(), hlab.numpy()
+        W0h = W0.cpu().numpy()
+        import ctypes
+
+        def e2e_step():
+            Xd = S.to_device_matrix(hXt, dev)  # H2D of the training subset
+            W = S.train_som(Xd, W0h, XD, YD, rlen=1, batches_per_pass=BATCHES, group=group,
+                            tile_offset=tile_offset)
+            Wh = W.cpu().numpy().astype(np.float32)  # D2H of the codebook
+            rc = lib.pixie_map_data_to_nodes_host_f32(
+                Wh.ctypes.data_as(ctypes.c_void_p), K, hXn.ctypes.data_as(ctypes.c_void_p), n, C,
+                hlabn.ctypes.data_as(ctypes.c_void_p), None, local, 1 << 20)
+            _native.check(rc, "pixie_map_data_to_nodes_host_f32")
+
+        e2e_step()
+        assert np.array_equal(hlabn[:262144], labels[:262144].cpu().numpy())
+        if distributed:
+            dist.barrier()
+        torch.cuda.synchronize()
+        e2e_steps = max(1, min(args.steps, 3))
+        t0 = time.perf_counter()
+        for _ in range(e2e_steps):
+            e2e_step()
+        torch.cuda.synchronize()
+        dt = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
+        if distributed:
+            dist.all_reduce(dt, op=dist.ReduceOp.MAX)
+        e2e = {"value": px_step * e2e_steps / float(dt), "unit": UNIT,
+               "h2d_bytes_per_step": int((n + ntrain) * C * 4 + K * C * 4),
+               "d2h_bytes_per_step": int(n * 4 + K * C * 8), "steps": e2e_steps,
+               "api": "som.train_som on an uploaded pinned matrix + "
+                      "pixie_map_data_to_nodes_host_f32 (pinned host rows in, host labels out)"}
+        del hX, hXt, hlab
+
+    # ---- CPU baseline beside it (rank 0, N = 1 only): bounded sample of the same workload
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu:
+        import oracle
+        oracle.build()
+        cores = len(os.sched_getaffinity(0))
+        Xs = X[:npx].cpu().numpy()  # one FOV of the same data
+        px, s, tr, a = cpu_sample_run(Xs, cores)
+        cpu = {"value": px / s, "unit": UNIT, "cores": cores, "kind": "port",
+               "sample": f"1 of {NFOV} FOVs ({npx} rows + its 10% subset): online SOM pass "
+                         f"(sequential, 1 thread) + map_data_to_nodes on {cores} threads in "
+                         f"1e6-row chunks; oracle/pixie_oracle.c (gcc -O2), {s:.1f} s",
+               "train_pixels_per_s": int(npx * SUBSET) / tr, "assign_pixels_per_s": npx / a}
+
+    if rank == 0:
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": max(args.warmup, 3), "ms_per_step": total_ms / args.steps,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "tf32+f32+f64",
+            "data": "synthetic", "config": workload_config(world),
+            "train_pixels_per_s": ntrain * world * args.steps / (train_ms * 1e-3),
+            "assign_pixels_per_s": n * world * args.steps / (assign_ms * 1e-3),
+            "train_ms_per_step": train_ms / args.steps, "assign_ms_per_step": assign_ms / args.steps,
+            "wall_ms_per_step": wall_ms / args.steps,
+            "rows_rechecked_frac": flagged_frac,
+            "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches),
+            "clocks": clocks,
+        }
+        print(json.dumps(line), flush=True)
+    if distributed:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-cpu", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_gpu(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -53,6 +53,8 @@ extern "C" {
 
 int pixie_version(void);
 const char *pixie_error_string(int code);
+/* kernels launched by this library in this process so far (bench.py's gpu_launches) */
+unsigned long long pixie_kernel_launches(void);
 /* number of CUDA devices visible, or a negative error */
 int pixie_device_count(void);
 

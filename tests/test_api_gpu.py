@@ -331,8 +331,8 @@ def test_train_cell_som_and_cluster_cells(tmp_path, capsys, normalize):
     df, cols = make_cell_table()
     table = os.path.join(base, 'cell_table.csv')
     df.to_csv(table, index=False)
-    pysom = cell_som_clustering.train_cell_som(['fov0', 'fov1'], base, table, cols, df * 1 if False
-                                               else df.copy(), normalize=normalize)
+    pysom = cell_som_clustering.train_cell_som(['fov0', 'fov1'], base, table, cols, df.copy(),
+                                               normalize=normalize)
     assert "Training SOM" in capsys.readouterr().out
     assert os.path.exists(os.path.join(base, 'cell_som_weights.feather'))
     assert pysom.weights.shape == (100, 15)
