@@ -455,7 +455,10 @@ bmu_tc_kernel(const __grid_constant__ CUtensorMap tmX, const TcParams p)
             // is two-sided and a node can only be the true minimum if its score is within 2E of
             // the smallest one.  When x and the codebook are both non-negative, operand truncation
             // can only RAISE a score (by at most E), so E suffices.
-            const float E = 0.00415039f * sqrtf(xn2) * 1.000001f * wmax + 3.8147e-6f * wmax2;
+            // The 1e-30 floors keep the bound meaningful when squares or products underflow (the
+            // error model above is relative): such rows simply collect candidates and end in fp64.
+            const float E = 0.00415039f * sqrtf(xn2 + 1.0e-30f) * 1.000001f * wmax +
+                            3.8147e-6f * wmax2 + 1.0e-30f;
             const float delta = (w_nonneg && (int32_t)sgn >= 0) ? 1.03125f * E : 2.0f * E;
 
             float m_run = __int_as_float(0x7f800000);

@@ -93,6 +93,13 @@ int num_sms_current_device()
     return cached[dev];
 }
 
+// CTAs of the cluster-sums kernel: one per SM (its grid barrier needs them co-resident)
+int sum_parts()
+{
+    const int sms = num_sms_current_device();
+    return sms < kSumParts ? sms : kSumParts;
+}
+
 // ---- workspace carve-up
 struct Workspace {
     float *wimg;
@@ -133,6 +140,8 @@ int bmu_tiles(const float *X, int64_t n, int C, int64_t ldX, const float *W, int
     bool use_tc = plan.ok && aligned && !(flags & PIXIE_FLAG_FORCE_EXACT);
     CUtensorMap tm;
     if (use_tc && !make_x_tensor_map(&tm, X, n, C, ldX)) use_tc = false;
+    // control block: norms, flags, fix-up counter, cluster-sums ticket
+    PX_CUDA(cudaMemsetAsync(ws.aux, 0, sizeof(CodebookAux), stream));
     if (!use_tc) {
         if (flags & PIXIE_FLAG_FORCE_TC) return PIXIE_ERR_UNSUPPORTED;
         PX_CUDA(launch_bmu_exact(X, n, C, ldX, W, K, labels, tile_first, tile_stride, ntiles,
@@ -143,7 +152,6 @@ int bmu_tiles(const float *X, int64_t n, int C, int64_t ldX, const float *W, int
         }
         return PIXIE_OK;
     }
-    PX_CUDA(cudaMemsetAsync(ws.aux, 0, sizeof(CodebookAux), stream));
     PX_CUDA(launch_codebook_prep(W, K, C, plan, ws.wimg, ws.aux, stream));
     TcParams p{};
     p.n = n;
@@ -224,7 +232,7 @@ int pixie_bmu_f32(const float *X, int64_t n, int32_t C, int64_t ldX, const float
     if (rc != PIXIE_OK) return rc;
     if (SN_or_null)
         PX_CUDA(launch_cluster_sums(X, n, C, ldX, labels, 0, K, 0, 1, ntiles, ws.partials,
-                                    kSumParts, SN_or_null, st));
+                                    sum_parts(), SN_or_null, ws.aux->sums_sync, st));
     return PIXIE_OK;
 }
 
@@ -244,8 +252,11 @@ int pixie_cluster_sums_f32(const float *X, int64_t n, int32_t C, int64_t ldX, co
     if (bad_shape(n, C, ldX, K) || !labels || !SN || (n > 0 && !X)) return PIXIE_ERR_INVALID_ARG;
     Workspace ws = carve(workspace, 0, C, K);
     if (!workspace || ws_bytes < ws.total) return PIXIE_ERR_WORKSPACE;
+    PX_CUDA(cudaMemsetAsync(ws.aux->sums_sync, 0, 2 * sizeof(unsigned int),
+                            reinterpret_cast<cudaStream_t>(stream)));
     PX_CUDA(launch_cluster_sums(X, n, C, ldX, labels, 0, K, 0, 1, (n + kTile - 1) / kTile,
-                                ws.partials, kSumParts, SN, reinterpret_cast<cudaStream_t>(stream)));
+                                ws.partials, sum_parts(), SN, ws.aux->sums_sync,
+                                reinterpret_cast<cudaStream_t>(stream)));
     return PIXIE_OK;
 }
 
@@ -267,7 +278,7 @@ int pixie_som_accum_f32(const float *X, int64_t n, int32_t C, int64_t ldX, const
                        ws, flags, stats_or_null, st);
     if (rc != PIXIE_OK) return rc;
     PX_CUDA(launch_cluster_sums(X, n, C, ldX, ws.labels_scratch, 1, K, tile_first, tile_stride,
-                                ntiles, ws.partials, kSumParts, SN, st));
+                                ntiles, ws.partials, sum_parts(), SN, ws.aux->sums_sync, st));
     return PIXIE_OK;
 }
 

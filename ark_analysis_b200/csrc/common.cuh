@@ -22,6 +22,8 @@ struct CodebookAux {
     int nonfinite;
     int fixup_count;  // rows the tensor-core kernel handed to the exact fix-up kernel
     int w_has_negative;  // any codebook entry with the sign bit set (disables the one-sided bound)
+    unsigned int sums_sync[2];  // grid barrier of the cluster-sums kernel (self-resetting)
+    int pad[2];
 };
 
 // Host-side plan of the tensor-core BMU kernel for one (C, K).
@@ -76,7 +78,8 @@ cudaError_t launch_bmu_dist(const float *X, int64_t n, int C, int64_t ldX, const
 cudaError_t launch_cluster_sums(const float *X, int64_t n, int C, int64_t ldX,
                                 const int32_t *labels, int compact_labels, int K,
                                 int64_t tile_first, int64_t tile_stride, int64_t ntiles,
-                                float *partials, int nparts, double *SN, cudaStream_t stream);
+                                float *partials, int nparts, double *SN, unsigned int *ticket,
+                                cudaStream_t stream);
 cudaError_t launch_som_apply(double *W64, float *W32, const double *SN, int xdim, int ydim, int C,
                              double sigma, double alpha, cudaStream_t stream);
 

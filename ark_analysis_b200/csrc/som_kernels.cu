@@ -12,9 +12,12 @@
 namespace pixie {
 
 // ------------------------------------------------------------------------------------------------
-// exact BMU: one thread per row; identical operation sequence to oracle/pixie_oracle.c
-// nearest_node() (cluster_helpers.py:152-157 semantics): fp64 subtract, multiply, add in channel
-// order (no FMA contraction), sqrt, strict '<', nodes in index order.
+// exact BMU: identical operation sequence to oracle/pixie_oracle.c nearest_node()
+// (cluster_helpers.py:152-157 semantics): fp64 subtract, multiply, add in channel order (no FMA
+// contraction), sqrt, strict '<', nodes in index order.  A warp takes 32 consecutive rows; every
+// row that needs work is then handled by the WHOLE warp -- lane l evaluates nodes l, l+32, ... and
+// keeps its first minimum; the lexicographic (distance, index) minimum over lanes is exactly the
+// first minimum of the sequential loop.
 // ------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(128)
 bmu_exact_kernel(const float *__restrict__ X, int64_t n, int C, int64_t ldX,
@@ -24,29 +27,47 @@ bmu_exact_kernel(const float *__restrict__ X, int64_t n, int C, int64_t ldX,
 {
     const bool fix_only = fixup_count != nullptr;
     if (fix_only && *fixup_count == 0) return;  // nothing was flagged: the common case
+    const int lane = threadIdx.x & 31;
     for (int64_t j = blockIdx.x; j < ntiles; j += gridDim.x) {
         const int64_t tile = tile_first + j * tile_stride;
         const int64_t row = tile * kTile + threadIdx.x;
         const int64_t lidx = compact_labels ? j * kTile + threadIdx.x : row;
-        if (row >= n) continue;
-        if (fix_only && labels[lidx] != kLabelFixup) continue;
-        const float *x = X + (size_t)row * ldX;
-        int minid = -1;
-        double mindist = DBL_MAX;
-        for (int k = 0; k < K; ++k) {
-            const float *w = W + (size_t)k * C;
-            double acc = 0.0;
-            for (int c = 0; c < C; ++c) {
-                const double tmp = __dsub_rn((double)x[c], (double)__ldg(w + c));
-                acc = __dadd_rn(acc, __dmul_rn(tmp, tmp));
+        bool todo = row < n;
+        if (todo && fix_only) todo = labels[lidx] == kLabelFixup;
+        unsigned work = __ballot_sync(0xffffffffu, todo);
+        while (work) {
+            const int src = __ffs(work) - 1;
+            work &= work - 1;
+            const int64_t r = row - lane + src;
+            const float *x = X + (size_t)r * ldX;
+            int minid = -1;
+            double mindist = DBL_MAX;
+            for (int k = lane; k < K; k += 32) {
+                const float *w = W + (size_t)k * C;
+                double acc = 0.0;
+                for (int c = 0; c < C; ++c) {
+                    const double tmp = __dsub_rn((double)__ldg(x + c), (double)__ldg(w + c));
+                    acc = __dadd_rn(acc, __dmul_rn(tmp, tmp));
+                }
+                const double d = __dsqrt_rn(acc);
+                if (d < mindist) {
+                    mindist = d;
+                    minid = k;
+                }
             }
-            const double d = __dsqrt_rn(acc);
-            if (d < mindist) {
-                mindist = d;
-                minid = k;
+            // lexicographic (distance, index) minimum; lanes without a finite candidate carry
+            // (DBL_MAX, INT_MAX) and never win against a real one
+            int bid = minid < 0 ? 0x7fffffff : minid;
+            for (int o = 16; o > 0; o >>= 1) {
+                const double od = __shfl_xor_sync(0xffffffffu, mindist, o);
+                const int oi = __shfl_xor_sync(0xffffffffu, bid, o);
+                if (od < mindist || (od == mindist && oi < bid)) {
+                    mindist = od;
+                    bid = oi;
+                }
             }
+            if (lane == src) labels[lidx] = (bid == 0x7fffffff) ? 0 : bid + 1;
         }
-        labels[lidx] = minid + 1;
     }
 }
 
@@ -99,40 +120,79 @@ cudaError_t launch_bmu_dist(const float *X, int64_t n, int C, int64_t ldX, const
 }
 
 // ------------------------------------------------------------------------------------------------
-// cluster sums.  Each CTA walks its tiles; per tile the 128 rows are counting-sorted by label in
-// shared memory, then each warp sums whole label segments (lanes = channels, fixed row order) and
-// adds the segment sum into the CTA's private fp32 partial buffer in global memory (L2-resident,
-// plain read-modify-write: a node's segment of one tile is owned by exactly one warp, and tiles are
-// separated by a CTA barrier, so no atomics and a fixed summation order).  A second kernel folds
-// the per-CTA partials into fp64 in fixed order => results are run-to-run deterministic.
+// cluster sums: SN[k] = [sum of the rows labelled k+1 | their count].
+//
+// Each CTA walks its tiles.  Per tile the 128 rows are staged in shared memory (coalesced), the
+// labels are counting-sorted with STABLE ranks (warp match + per-warp counts, so the order inside a
+// node's segment is the row order whatever the scheduling), then each warp sums whole segments with
+// lanes = channels and adds the segment sum into the CTA's fp32 accumulator -- in shared memory when
+// K x (C+1) fits (a segment is owned by one warp and tiles are separated by a CTA barrier: no
+// atomics, fixed order), else in the CTA's private slice of a global scratch.  The CTA's totals go
+// to partials[cta]; the LAST CTA to finish (atomic ticket) folds all partials into SN in fp64 in
+// CTA order, so the result is run-to-run deterministic and no second launch is needed.
 // partials layout: [nparts][K][C+1] fp32 (last column = count).
 // ------------------------------------------------------------------------------------------------
 constexpr int kSumThreads = 256;
+constexpr int kSumWarps = kSumThreads / 32;
 
+template <bool kSmemAcc>
 __global__ void __launch_bounds__(kSumThreads)
 cluster_sums_kernel(const float *__restrict__ X, int64_t n, int C, int64_t ldX,
                     const int32_t *__restrict__ labels, int compact_labels, int K,
                     int64_t tile_first, int64_t tile_stride, int64_t ntiles,
-                    float *__restrict__ partials)
+                    float *__restrict__ partials, double *__restrict__ SN, unsigned int *sync)
 {
-    extern __shared__ int s_int[];
-    int *s_cnt = s_int;            // [K]   rows per node in this tile
-    int *s_start = s_cnt + K;      // [K+1] segment starts
-    int *s_lab = s_start + K + 1;  // [128] label-1 per row (-1 = skip)
-    int *s_rank = s_lab + kTile;   // [128] rank of the row within its node
-    int *s_perm = s_rank + kTile;  // [128] rows sorted by node
-    int *s_seg = s_perm + kTile;   // [128] list of non-empty nodes
+    extern __shared__ __align__(16) unsigned char s_raw[];
+    const int len = K * (C + 1);
+    // layout: [tile rows 128 x Cp fp32][acc (optional) len fp32][ints]
+    const int Cp = (C + 3) & ~3;
+    float *s_tile = reinterpret_cast<float *>(s_raw);
+    float *s_acc = s_tile + kTile * Cp;
+    int *s_int = reinterpret_cast<int *>(s_acc + (kSmemAcc ? len : 0));
+    int *s_wcnt = s_int;                 // [4][K] rows per (row-warp, node) in this tile
+    int *s_start = s_wcnt + 4 * K;       // [K+1] segment starts
+    int *s_lab = s_start + K + 1;        // [128] label-1 per row (-1 = skip)
+    int *s_rank = s_lab + kTile;         // [128] stable rank of the row within its node
+    int *s_perm = s_rank + kTile;        // [128] rows sorted by node
+    int *s_seg = s_perm + kTile;         // [128] list of non-empty nodes
     __shared__ int s_nseg;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    const int nwarps = kSumThreads / 32;
-    float *mine = partials + (size_t)blockIdx.x * K * (C + 1);
-    for (int i = tid; i < K * (C + 1); i += kSumThreads) mine[i] = 0.f;
+    float *mine = partials + (size_t)blockIdx.x * len;
+    float *acc = kSmemAcc ? s_acc : mine;
+    for (int i = tid; i < len; i += kSumThreads) acc[i] = 0.f;
     __syncthreads();
 
     for (int64_t j = blockIdx.x; j < ntiles; j += gridDim.x) {
         const int64_t tile = tile_first + j * tile_stride;
         const int64_t row0 = tile * kTile;
-        for (int i = tid; i < K; i += kSumThreads) s_cnt[i] = 0;
+        // stage the tile (rows past n are never referenced)
+        {
+            const int vec_per_row = Cp >> 2;
+            const bool vec_ok = ((ldX & 3) == 0) && ((reinterpret_cast<uintptr_t>(X) & 15) == 0);
+            if (vec_ok) {
+                for (int i = tid; i < kTile * vec_per_row; i += kSumThreads) {
+                    const int r = i / vec_per_row, v = i - r * vec_per_row;
+                    float4 val = make_float4(0.f, 0.f, 0.f, 0.f);
+                    if (row0 + r < n) {
+                        const float *src = X + (size_t)(row0 + r) * ldX + 4 * v;
+                        if (4 * v + 3 < C) {
+                            val = __ldg(reinterpret_cast<const float4 *>(src));
+                        } else {
+                            if (4 * v + 0 < C) val.x = __ldg(src + 0);
+                            if (4 * v + 1 < C) val.y = __ldg(src + 1);
+                            if (4 * v + 2 < C) val.z = __ldg(src + 2);
+                        }
+                    }
+                    reinterpret_cast<float4 *>(s_tile)[i] = val;
+                }
+            } else {
+                for (int i = tid; i < kTile * Cp; i += kSumThreads) {
+                    const int r = i / Cp, c = i - r * Cp;
+                    s_tile[i] = (row0 + r < n && c < C) ? __ldg(X + (size_t)(row0 + r) * ldX + c) : 0.f;
+                }
+            }
+        }
+        for (int i = tid; i < 4 * K; i += kSumThreads) s_wcnt[i] = 0;
         __syncthreads();
         if (tid < kTile) {
             const int64_t row = row0 + tid;
@@ -142,24 +202,19 @@ cluster_sums_kernel(const float *__restrict__ X, int64_t n, int C, int64_t ldX,
                 if (lab < 0 || lab >= K) lab = -1;
             }
             s_lab[tid] = lab;
+            // stable rank inside the warp: earlier lanes with the same label
+            const unsigned peers = __match_any_sync(0xffffffffu, lab);
+            const int rank_w = __popc(peers & ((1u << lane) - 1u));
+            s_rank[tid] = rank_w;
+            if (lab >= 0 && rank_w == 0) s_wcnt[warp * K + lab] = __popc(peers);
         }
         __syncthreads();
-        // ranks must not depend on thread scheduling: row order within a node is the row index.
-        if (tid < kTile) {
-            const int lab = s_lab[tid];
-            int rank = 0;
-            if (lab >= 0) {
-                for (int t = 0; t < tid; ++t) rank += (s_lab[t] == lab);
-                atomicAdd(&s_cnt[lab], 1);
-            }
-            s_rank[tid] = rank;
-        }
-        __syncthreads();
-        if (warp == 0) {  // exclusive scan of s_cnt and list of non-empty nodes, in node order
+        if (warp == 0) {  // exclusive scan over nodes of the per-node totals, list of non-empty nodes
             int carry = 0, nseg = 0;
             for (int base = 0; base < K; base += 32) {
                 const int k = base + lane;
-                const int c = k < K ? s_cnt[k] : 0;
+                int c = 0;
+                if (k < K) c = s_wcnt[k] + s_wcnt[K + k] + s_wcnt[2 * K + k] + s_wcnt[3 * K + k];
                 int incl = c;
                 for (int o = 1; o < 32; o <<= 1) {
                     const int t = __shfl_up_sync(~0u, incl, o);
@@ -177,54 +232,110 @@ cluster_sums_kernel(const float *__restrict__ X, int64_t n, int C, int64_t ldX,
             }
         }
         __syncthreads();
-        if (tid < kTile && s_lab[tid] >= 0) s_perm[s_start[s_lab[tid]] + s_rank[tid]] = tid;
+        if (tid < kTile) {
+            const int lab = s_lab[tid];
+            if (lab >= 0) {
+                int before = 0;  // rows of the same node in earlier row-warps
+                for (int w = 0; w < warp; ++w) before += s_wcnt[w * K + lab];
+                s_perm[s_start[lab] + before + s_rank[tid]] = tid;
+            }
+        }
         __syncthreads();
         const int nseg = s_nseg;
-        for (int sg = warp; sg < nseg; sg += nwarps) {
+        for (int sg = warp; sg < nseg; sg += kSumWarps) {
             const int k = s_seg[sg];
-            const int lo = s_start[k], hi = lo + s_cnt[k];
-            float *dst = mine + (size_t)k * (C + 1);
+            const int lo = s_start[k], hi = s_start[k + 1];
+            float *dst = acc + (size_t)k * (C + 1);
             for (int c0 = 0; c0 < C; c0 += 32) {
                 const int c = c0 + lane;
                 if (c < C) {
-                    float acc = 0.f;
-                    for (int q = lo; q < hi; ++q)
-                        acc += __ldg(X + (size_t)(row0 + s_perm[q]) * ldX + c);
-                    dst[c] += acc;
+                    float a = 0.f;
+                    for (int q = lo; q < hi; ++q) a += s_tile[s_perm[q] * Cp + c];
+                    dst[c] += a;
                 }
             }
             if (lane == 0) dst[C] += (float)(hi - lo);
         }
         __syncthreads();
     }
-}
-
-// SN[i] = sum over parts (fixed order, fp64) of partials[part][i]
-__global__ void reduce_partials_kernel(const float *__restrict__ partials, int nparts, int len,
-                                       double *__restrict__ SN)
-{
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= len) return;
-    double acc = 0.0;
-    for (int p = 0; p < nparts; ++p) acc += (double)partials[(size_t)p * len + i];
-    SN[i] = acc;
+    if (kSmemAcc)
+        for (int i = tid; i < len; i += kSumThreads) mine[i] = s_acc[i];
+    // ---- grid barrier (all CTAs are co-resident: grid <= SM count, one CTA per SM fits), then
+    // every CTA folds its slice of the K x (C+1) table over all partials in CTA order, in fp64:
+    // deterministic, parallel, and no second launch.
+    __threadfence();
+    __syncthreads();
+    if (tid == 0) {
+        atomicAdd(&sync[0], 1u);
+        unsigned spins = 0;
+        while (atomicAdd(&sync[0], 0u) < gridDim.x) {
+            __nanosleep(64);
+            if (++spins > (1u << 24)) __trap();  // ~2 s: never on a healthy launch
+        }
+    }
+    __syncthreads();
+    __threadfence();
+    {
+        const int nparts = gridDim.x;
+        const int per = (len + nparts - 1) / nparts;
+        const int e0 = blockIdx.x * per;
+        const int e1 = min(len, e0 + per);
+        // 8 threads per element: thread q of the octet sums partials q, q+8, ... (ascending), the
+        // octet is then combined in a fixed shuffle tree
+        const int oct = tid >> 3, q = tid & 7;
+        const int rounds = (per + kSumThreads / 8 - 1) / (kSumThreads / 8);  // uniform trip count
+        for (int it = 0; it < rounds; ++it) {
+            const int e = e0 + it * (kSumThreads / 8) + oct;
+            double a = 0.0;
+            if (e < e1)
+                for (int p = q; p < nparts; p += 8) a += (double)__ldcg(partials + (size_t)p * len + e);
+            a += __shfl_xor_sync(0xffffffffu, a, 1);
+            a += __shfl_xor_sync(0xffffffffu, a, 2);
+            a += __shfl_xor_sync(0xffffffffu, a, 4);
+            if (e < e1 && q == 0) SN[e] = a;
+        }
+    }
+    __syncthreads();
+    if (tid == 0) {
+        // the last CTA to leave re-arms the barrier for the next launch on this stream
+        if (atomicAdd(&sync[1], 1u) == gridDim.x - 1) {
+            sync[0] = 0u;
+            sync[1] = 0u;
+            __threadfence();
+        }
+    }
 }
 
 cudaError_t launch_cluster_sums(const float *X, int64_t n, int C, int64_t ldX,
                                 const int32_t *labels, int compact_labels, int K,
                                 int64_t tile_first, int64_t tile_stride, int64_t ntiles,
-                                float *partials, int nparts, double *SN, cudaStream_t stream)
+                                float *partials, int nparts, double *SN, unsigned int *ticket,
+                                cudaStream_t stream)
 {
     const int len = K * (C + 1);
-    const size_t smem = (size_t)(K + K + 1 + 4 * kTile) * sizeof(int);
-    // every partial buffer is (re)initialised by its CTA, so always launch all nparts CTAs
-    cluster_sums_kernel<<<nparts, kSumThreads, smem, stream>>>(X, n, C, ldX, labels,
-                                                              compact_labels, K, tile_first,
-                                                              tile_stride, ntiles, partials);
-    count_launch();
-    cudaError_t e = cudaGetLastError();
-    if (e != cudaSuccess) return e;
-    reduce_partials_kernel<<<(len + 255) / 256, 256, 0, stream>>>(partials, nparts, len, SN);
+    const int Cp = (C + 3) & ~3;
+    const size_t ints = (size_t)(4 * K + K + 1 + 4 * kTile) * sizeof(int);
+    const size_t tile_bytes = (size_t)kTile * Cp * sizeof(float);
+    const size_t smem_acc = tile_bytes + (size_t)len * sizeof(float) + ints;
+    const size_t smem_noacc = tile_bytes + ints;
+    int grid = nparts;
+    if ((int64_t)grid > ntiles) grid = ntiles > 0 ? (int)ntiles : 1;
+    cudaError_t e;
+    if (smem_acc <= 200 * 1024) {
+        e = cudaFuncSetAttribute(cluster_sums_kernel<true>,
+                                 cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_acc);
+        if (e != cudaSuccess) return e;
+        cluster_sums_kernel<true><<<grid, kSumThreads, smem_acc, stream>>>(
+            X, n, C, ldX, labels, compact_labels, K, tile_first, tile_stride, ntiles, partials, SN,
+            ticket);
+    } else {
+        e = cudaFuncSetAttribute(cluster_sums_kernel<false>,
+                                 cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_noacc);
+        if (e != cudaSuccess) return e;
+        cluster_sums_kernel<false><<<grid, kSumThreads, smem_noacc, stream>>>(
+            X, n, C, ldX, labels, compact_labels, K, tile_first, tile_stride, ntiles, partials, SN,
+            ticket);
+    }
     count_launch();
     return cudaGetLastError();
 }
@@ -233,39 +344,33 @@ cudaError_t launch_cluster_sums(const float *X, int64_t n, int C, int64_t ldX,
 // batch-SOM update (fp64 restatement in oracle/pixie_oracle.c
 // oracle_som_batch).  One CTA per node k, threads over channels.
 // ------------------------------------------------------------------------------------------------
-__global__ void som_apply_kernel(double *__restrict__ W64, float *__restrict__ W32,
-                                 const double *__restrict__ SN, int xdim, int ydim, int C,
-                                 double inv2s2, double alpha)
+__global__ void __launch_bounds__(128)
+som_apply_kernel(double *__restrict__ W64, float *__restrict__ W32, const double *__restrict__ SN,
+                 int xdim, int ydim, int C, double inv2s2, double alpha)
 {
+    extern __shared__ double s_dyn[];
     const int K = xdim * ydim;
+    double *s_h = s_dyn;       // [K] H[k, b] * (n_b > 0) for this CTA's node k
+    double *s_cnt = s_h + K;   // [K] n_b
     const int k = blockIdx.x;
     const int kx = k / ydim, ky = k % ydim;
-    __shared__ double s_den;
-    if (threadIdx.x == 0) {
-        double den = 0.0;
-        for (int b = 0; b < K; ++b) {
-            const double cnt = SN[(size_t)b * (C + 1) + C];
-            if (cnt == 0.0) continue;
-            const int dx = abs(kx - b / ydim), dy = abs(ky - b % ydim);
-            const double d = (double)(dx > dy ? dx : dy);
-            den += exp(-d * d * inv2s2) * cnt;
-        }
-        s_den = den;
+    for (int b = threadIdx.x; b < K; b += blockDim.x) {
+        const int dx = abs(kx - b / ydim), dy = abs(ky - b % ydim);
+        const double d = (double)(dx > dy ? dx : dy);
+        const double cnt = SN[(size_t)b * (C + 1) + C];
+        s_cnt[b] = cnt;
+        s_h[b] = cnt == 0.0 ? 0.0 : exp(-d * d * inv2s2);  // empty nodes are skipped, as the oracle does
     }
     __syncthreads();
-    const double den = s_den;
+    // den_k = sum_b H[k,b] n_b in node order (every thread computes it: K is a few hundred)
+    double den = 0.0;
+    for (int b = 0; b < K; ++b) den += s_h[b] * s_cnt[b];
+    const double beta = den > 0.0 ? 1.0 - pow(1.0 - alpha, den) : 0.0;
     for (int c = threadIdx.x; c < C; c += blockDim.x) {
         double w = W64[(size_t)k * C + c];
         if (den > 0.0) {
             double num = 0.0;
-            for (int b = 0; b < K; ++b) {
-                const double cnt = SN[(size_t)b * (C + 1) + C];
-                if (cnt == 0.0) continue;
-                const int dx = abs(kx - b / ydim), dy = abs(ky - b % ydim);
-                const double d = (double)(dx > dy ? dx : dy);
-                num += exp(-d * d * inv2s2) * SN[(size_t)b * (C + 1) + c];
-            }
-            const double beta = 1.0 - pow(1.0 - alpha, den);
+            for (int b = 0; b < K; ++b) num += s_h[b] * __ldg(SN + (size_t)b * (C + 1) + c);
             w += beta * (num / den - w);
             W64[(size_t)k * C + c] = w;
         }
@@ -277,7 +382,9 @@ cudaError_t launch_som_apply(double *W64, float *W32, const double *SN, int xdim
                              double sigma, double alpha, cudaStream_t stream)
 {
     const double inv2s2 = 1.0 / (2.0 * sigma * sigma);
-    som_apply_kernel<<<xdim * ydim, 128, 0, stream>>>(W64, W32, SN, xdim, ydim, C, inv2s2, alpha);
+    const int K = xdim * ydim;
+    som_apply_kernel<<<K, 128, (size_t)2 * K * sizeof(double), stream>>>(W64, W32, SN, xdim, ydim, C,
+                                                                      inv2s2, alpha);
     count_launch();
     return cudaGetLastError();
 }

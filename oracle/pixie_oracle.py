@@ -102,7 +102,9 @@ def map_data_to_nodes_mt(nodes, newdata, nthreads):
 def map_data_to_nodes_f32(nodes32, data32):
     """Same arithmetic on fp32 inputs promoted to fp64 (the parity protocol)."""
     nodes32 = np.ascontiguousarray(nodes32, np.float32)
-    assert data32.dtype == np.float32 and data32.ndim == 2 and data32.strides[1] == 4
+    assert data32.dtype == np.float32 and data32.ndim == 2
+    if data32.shape[0] > 1 and data32.strides[1] != 4:
+        data32 = np.ascontiguousarray(data32)
     m, C = data32.shape
     ld = data32.strides[0] // 4 if m > 1 else C
     labels = np.empty(m, np.int32)
@@ -135,7 +137,9 @@ def som_online(data, xdim=10, ydim=10, rlen=10, alpha_range=(0.05, 0.01), radius
 def som_batch(data32, xdim=10, ydim=10, rlen=1, alpha_range=(0.05, 0.01), radius_range=None,
               seed=42, batches_per_pass=None, init_idx=None):
     """fp64 restatement of the batch SOM the B200 path runs."""
-    assert data32.dtype == np.float32 and data32.ndim == 2 and data32.strides[1] == 4
+    assert data32.dtype == np.float32 and data32.ndim == 2
+    if data32.shape[0] > 1 and data32.strides[1] != 4:
+        data32 = np.ascontiguousarray(data32)
     n, C = data32.shape
     ld = data32.strides[0] // 4 if n > 1 else C
     K = xdim * ydim
@@ -153,7 +157,9 @@ def som_batch(data32, xdim=10, ydim=10, rlen=1, alpha_range=(0.05, 0.01), radius
 
 
 def cluster_sums_f32(data32, labels, K):
-    assert data32.dtype == np.float32 and data32.ndim == 2 and data32.strides[1] == 4
+    assert data32.dtype == np.float32 and data32.ndim == 2
+    if data32.shape[0] > 1 and data32.strides[1] != 4:
+        data32 = np.ascontiguousarray(data32)
     n, C = data32.shape
     ld = data32.strides[0] // 4 if n > 1 else C
     labels = np.ascontiguousarray(labels, np.int32)

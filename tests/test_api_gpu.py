@@ -85,7 +85,7 @@ class TestPixelSOMCluster:
         with warnings.catch_warnings():
             warnings.simplefilter("error")
             pysom.train_som()
-        X = pysom.train_data[self.chans].to_numpy().astype(np.float32)
+        X = np.ascontiguousarray(pysom.train_data[self.chans].to_numpy(), np.float32)
         ref = oracle.som_batch(X, 20, 10, rlen=1, seed=7)
         assert np.abs(pysom.weights.values - ref).max() / np.abs(ref).max() < 1e-4
 
@@ -102,7 +102,7 @@ class TestPixelSOMCluster:
         assert pysom.som_clusters_seen == set(np.unique(labels).tolist())
         np.testing.assert_allclose(out[self.chans].values, ext[self.chans].values / 0.5)
         # parity with the oracle on the normalised fp32 values
-        Xn = (ext[self.chans].values / 0.5).astype(np.float32)
+        Xn = np.ascontiguousarray(ext[self.chans].values / 0.5, np.float32)
         ref, _ = oracle.map_data_to_nodes_f32(pysom.weights.values.astype(np.float32), Xn)
         np.testing.assert_array_equal(labels, ref)
         # shuffled columns give the same labels (columns follow the weights' order)
@@ -171,7 +171,7 @@ def test_cluster_pixels_base(tmp_path, capsys, multiprocess):
     out = capsys.readouterr().out
     assert "Mapping pixel data to SOM cluster labels" in out and "Processed 3 fovs" in out
     assert not os.path.exists(os.path.join(base, 'pixel_mat_data_temp'))
-    W32 = pysom.weights.values.astype(np.float32)
+    W32 = np.ascontiguousarray(pysom.weights.values, np.float32)
     seen = set()
     for fov in FOVS:
         df = io_utils.read_dataframe(os.path.join(base, 'pixel_mat_data', fov + '.feather'))
@@ -179,7 +179,8 @@ def test_cluster_pixels_base(tmp_path, capsys, multiprocess):
         assert np.all(labels <= 100) and np.all(labels >= 1)
         # the stored table holds the NORMALISED channels plus the labels (reference :289-301)
         np.testing.assert_allclose(df[CHANS].values, raw[fov][CHANS].values / 0.5)
-        ref, _ = oracle.map_data_to_nodes_f32(W32, (raw[fov][CHANS].values / 0.5).astype(np.float32))
+        ref, _ = oracle.map_data_to_nodes_f32(
+            W32, np.ascontiguousarray(raw[fov][CHANS].values / 0.5, np.float32))
         np.testing.assert_array_equal(labels, ref)
         seen |= set(np.unique(labels).tolist())
     assert pysom.som_clusters_seen == seen  # kept even with multiprocess=True
@@ -345,7 +346,7 @@ def test_train_cell_som_and_cluster_cells(tmp_path, capsys, normalize):
     assert "Mapping cell data to SOM cluster labels" in capsys.readouterr().out
     labels = out['cell_som_cluster'].to_numpy()
     assert labels.min() >= 1 and labels.max() <= 100
-    X = pysom.cell_data[cols].to_numpy().astype(np.float32)
+    X = np.ascontiguousarray(pysom.cell_data[cols].to_numpy(), np.float32)
     ref, _ = oracle.map_data_to_nodes_f32(pysom.weights.values.astype(np.float32), X)
     np.testing.assert_array_equal(labels, ref)
     # idempotent without overwrite, reassigns with it
