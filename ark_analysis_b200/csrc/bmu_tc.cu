@@ -50,7 +50,7 @@ const Variant kVariants[] = {
 };
 }  // namespace
 
-TcPlan make_tc_plan(int C, int K)
+TcPlan make_tc_plan(int C, int K, bool acc)
 {
     TcPlan best{};
     best.ok = false;
@@ -82,7 +82,14 @@ TcPlan make_tc_plan(int C, int K)
         p.wimg_bytes = (uint32_t)p.nblkW * (uint32_t)p.Ntot * 128u;
         p.off_ones = p.wimg_bytes;
         p.off_x = p.off_ones + 4096u;
-        const uint32_t scratch = 256u + (uint32_t)(4 * v.NG) * kWarpPairCap * 8u;
+        // fused accumulation: one fp32 table per epilogue group + the tile's labels per group;
+        // the (C+1) columns are split over the 4 warps of a group, 32 lanes each
+        if (acc && (C + 1 + 3) / 4 > 32) continue;
+        const uint32_t acc_bytes =
+            acc ? ((uint32_t)v.NG * (uint32_t)K * (uint32_t)(C + 1) * 4u + 15u) / 16u * 16u +
+                      (uint32_t)v.NG * 512u
+                : 0u;
+        const uint32_t scratch = 256u + (uint32_t)(4 * v.NG) * kWarpPairCap * 8u + acc_bytes;
         const uint32_t limit = 227u * 1024u - 1024u;
         if (p.off_x + scratch + (uint32_t)v.NG * p.stage_bytes > limit) continue;
         p.nstage = (int)((limit - p.off_x - scratch) / p.stage_bytes);
@@ -92,7 +99,10 @@ TcPlan make_tc_plan(int C, int K)
         p.nstage = p.nstage / v.NG * v.NG;
         p.off_bar = p.off_x + (uint32_t)p.nstage * p.stage_bytes;
         p.off_pairs = p.off_bar + 256u;
-        p.smem_bytes = p.off_pairs + (uint32_t)(4 * v.NG) * kWarpPairCap * 8u + 1024u;
+        p.off_acc = p.off_pairs + (uint32_t)(4 * v.NG) * kWarpPairCap * 8u;
+        p.off_lab = p.off_acc + (acc_bytes ? acc_bytes - (uint32_t)v.NG * 512u : 0u);
+        p.acc = acc ? 1 : 0;
+        p.smem_bytes = p.off_acc + acc_bytes + 1024u;
         p.ok = true;
         // fewest padded codebook rows first; then more epilogue groups; then deeper pipeline
         const long cost = (long)(p.Nchunk * v.NCH) * 1000 - v.NG * 10 - p.nstage;
@@ -318,6 +328,10 @@ bmu_tc_kernel(const __grid_constant__ CUtensorMap tmX, const TcParams p)
         tmem_relinquish();
     }
     for (int i = threadIdx.x; i < 1024; i += blockDim.x) reinterpret_cast<float *>(ones)[i] = 1.0f;
+    if (p.partials != nullptr) {
+        float *a = reinterpret_cast<float *>(smem + pl.off_acc);
+        for (int i = threadIdx.x; i < NG * pl.K * (pl.C + 1); i += blockDim.x) a[i] = 0.f;
+    }
     fence_proxy_async();  // the ones tile is read by the tensor core (async proxy)
     tc_fence_before();
     __syncthreads();
@@ -406,6 +420,12 @@ bmu_tc_kernel(const __grid_constant__ CUtensorMap tmX, const TcParams p)
         const float wmax = __int_as_float(p.ctl->wmax_bits);
         const float wmax2 = wmax * wmax;
         const bool w_nonneg = p.ctl->w_has_negative == 0;
+        // fused accumulation (train mode)
+        const bool do_acc = p.partials != nullptr;
+        const int acc_ld = pl.C + 1;
+        const int acc_cq = (pl.C + 1 + 3) / 4;  // columns per warp of the group (<= 32)
+        float *acc_tab = reinterpret_cast<float *>(smem + pl.off_acc) + (size_t)g * pl.K * acc_ld;
+        int *acc_lab = reinterpret_cast<int *>(smem + pl.off_lab) + g * kTile;
 
         // stage / phase bookkeeping of this group's tile sequence (it = g, g+NG, ...)
         int s = g % nstage;
@@ -651,6 +671,36 @@ bmu_tc_kernel(const __grid_constant__ CUtensorMap tmX, const TcParams p)
             } else if (p.compact_labels) {
                 *lab_ptr = 0;  // padding row of the last tile: never counted
             }
+            if (do_acc) {
+                // ---- fused per-node sums: the group's 4 warps split the C+1 columns (channels +
+                // count); each warp walks the tile's 128 rows IN ROW ORDER with plain
+                // read-modify-writes on the group's private table (no atomics: a column belongs to
+                // one lane), so the sums are deterministic.  Fix-up rows are added by the exact
+                // kernel afterwards.
+                acc_lab[row] = (grow < p.n && label > 0) ? label - 1 : -1;
+                bar_sync(1u + (uint32_t)g, 128);
+                const int col = quad * acc_cq + lane;  // column of the K x (C+1) table
+                if (lane < acc_cq && col <= pl.C) {
+                    const bool is_cnt = col == pl.C;
+                    // byte offset of channel `col` inside a tile row, before the row swizzle
+                    const uint32_t blk_off = (uint32_t)(col >> 5) * 16384u;
+                    const uint32_t chunk = (uint32_t)(col & 31) >> 2, within = (uint32_t)(col & 3) * 4u;
+                    const uint8_t *xb = xs + blk_off + within;
+                    float *tab = acc_tab + col;
+#pragma unroll 4
+                    for (int r = 0; r < kTile; ++r) {
+                        const int lab = acc_lab[r];
+                        if (lab >= 0) {
+                            const float v =
+                                is_cnt ? 1.0f
+                                       : *reinterpret_cast<const float *>(
+                                             xb + (uint32_t)r * 128u + ((chunk ^ ((uint32_t)r & 7u)) << 4));
+                            tab[lab * acc_ld] += v;
+                        }
+                    }
+                }
+                bar_sync(1u + (uint32_t)g, 128);  // acc_lab is rewritten by the next tile
+            }
             // all reads of this X stage by this warp are done
             __syncwarp();
             if (lane == 0) mbar_arrive(bar_empty + 8u * s);
@@ -685,6 +735,61 @@ bmu_tc_kernel(const __grid_constant__ CUtensorMap tmX, const TcParams p)
     if (warp == NEPI + 1) {
         tc_fence_after();
         tmem_dealloc(tmem_base, (uint32_t)pl.tmem_cols);
+    }
+    if (p.partials != nullptr) {
+        // ---- fused sums, part 2: groups are combined in group order into this CTA's partial,
+        // then (grid barrier; every CTA is resident: grid <= SM count, one CTA per SM) each CTA
+        // folds its slice of the table over all partials in CTA order, in fp64.
+        const int len = pl.K * (pl.C + 1);
+        const float *a = reinterpret_cast<const float *>(smem + pl.off_acc);
+        float *mine = p.partials + (size_t)blockIdx.x * len;
+        for (int i = threadIdx.x; i < len; i += blockDim.x) {
+            float v = a[i];
+#pragma unroll
+            for (int gg = 1; gg < NG; ++gg) v += a[gg * len + i];
+            mine[i] = v;
+        }
+        unsigned int *sync = p.ctl->sums_sync;
+        __threadfence();
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            atomicAdd(&sync[0], 1u);
+            unsigned spins = 0;
+            while (atomicAdd(&sync[0], 0u) < gridDim.x) {
+                __nanosleep(64);
+                if (++spins > (1u << 24)) __trap();
+            }
+        }
+        __syncthreads();
+        __threadfence();
+        {
+            const int nparts = gridDim.x;
+            const int per = (len + nparts - 1) / nparts;
+            const int e0 = blockIdx.x * per;
+            const int e1 = min(len, e0 + per);
+            const int nthr = blockDim.x;           // multiple of 32
+            const int oct = threadIdx.x >> 3, q = threadIdx.x & 7;
+            const int rounds = (per + nthr / 8 - 1) / (nthr / 8);  // uniform trip count
+            for (int it = 0; it < rounds; ++it) {
+                const int e = e0 + it * (nthr / 8) + oct;
+                double acc = 0.0;
+                if (e < e1)
+                    for (int pp = q; pp < nparts; pp += 8)
+                        acc += (double)__ldcg(p.partials + (size_t)pp * len + e);
+                acc += __shfl_xor_sync(0xffffffffu, acc, 1);
+                acc += __shfl_xor_sync(0xffffffffu, acc, 2);
+                acc += __shfl_xor_sync(0xffffffffu, acc, 4);
+                if (e < e1 && q == 0) p.SN[e] = acc;
+            }
+        }
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            if (atomicAdd(&sync[1], 1u) == gridDim.x - 1) {
+                sync[0] = 0u;
+                sync[1] = 0u;
+                __threadfence();
+            }
+        }
     }
 }
 

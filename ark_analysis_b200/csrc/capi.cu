@@ -127,52 +127,67 @@ Workspace carve(void *base, int64_t n_visit, int C, int K)
     return w;
 }
 
-// BMU over the tiles {tile_first + j * tile_stride}, j < ntiles.
+// BMU over the tiles {tile_first + j * tile_stride}, j < ntiles.  When SN != null the per-node sums
+// and counts of the visited rows are produced as well: fused into the tensor-core kernel when the
+// accumulators fit in shared memory, else by the cluster-sums kernel behind it.
 int bmu_tiles(const float *X, int64_t n, int C, int64_t ldX, const float *W, int K,
               int32_t *labels, int compact, int64_t tile_first, int64_t tile_stride,
               int64_t ntiles, const Workspace &ws, uint32_t flags, unsigned long long *stats,
-              cudaStream_t stream)
+              double *SN, cudaStream_t stream)
 {
-    if (ntiles <= 0) return PIXIE_OK;
-    TcPlan plan = make_tc_plan(C, K);
+    if (ntiles <= 0) {
+        if (SN) PX_CUDA(cudaMemsetAsync(SN, 0, sizeof(double) * (size_t)K * (C + 1), stream));
+        return PIXIE_OK;
+    }
+    TcPlan plan = make_tc_plan(C, K, SN != nullptr);
+    bool fused = SN != nullptr && plan.ok;
+    if (!plan.ok && SN != nullptr) plan = make_tc_plan(C, K, false);
     const bool aligned = ((reinterpret_cast<uintptr_t>(X) & 15u) == 0) && (ldX % 4 == 0) &&
                          ldX >= C && n < ((int64_t)1 << 31) - kTile;
     bool use_tc = plan.ok && aligned && !(flags & PIXIE_FLAG_FORCE_EXACT);
     CUtensorMap tm;
     if (use_tc && !make_x_tensor_map(&tm, X, n, C, ldX)) use_tc = false;
-    // control block: norms, flags, fix-up counter, cluster-sums ticket
+    // control block: norms, flags, fix-up counter, grid-barrier words
     PX_CUDA(cudaMemsetAsync(ws.aux, 0, sizeof(CodebookAux), stream));
     if (!use_tc) {
         if (flags & PIXIE_FLAG_FORCE_TC) return PIXIE_ERR_UNSUPPORTED;
         PX_CUDA(launch_bmu_exact(X, n, C, ldX, W, K, labels, tile_first, tile_stride, ntiles,
-                                 compact, nullptr, stream));
+                                 compact, nullptr, nullptr, stream));
         if (stats) {
             set_u64_kernel<<<1, 1, 0, stream>>>(stats + PIXIE_STAT_KERNEL, 2ull);
             count_launch();
         }
-        return PIXIE_OK;
+        fused = false;
+    } else {
+        PX_CUDA(launch_codebook_prep(W, K, C, plan, ws.wimg, ws.aux, stream));
+        TcParams p{};
+        p.n = n;
+        p.tile_first = tile_first;
+        p.tile_stride = tile_stride;
+        p.ntiles = ntiles;
+        p.wimg = ws.wimg;
+        p.labels = labels;
+        p.compact_labels = compact;
+        p.stats = stats;
+        p.ctl = ws.aux;
+        p.partials = fused ? ws.partials : nullptr;
+        p.SN = fused ? SN : nullptr;
+        p.plan = plan;
+        PX_CUDA(launch_bmu_tc(tm, p, sum_parts(), stream));
+        // rows the tensor-core kernel could not settle (NaN/Inf rows, degenerate codebooks): exact
+        // kernel; returns immediately when the counter is zero.  In fused mode it also adds those
+        // rows to SN.
+        PX_CUDA(launch_bmu_exact(X, n, C, ldX, W, K, labels, tile_first, tile_stride, ntiles,
+                                 compact, &ws.aux->fixup_count, fused ? SN : nullptr, stream));
+        if (stats) {
+            set_u64_kernel<<<1, 1, 0, stream>>>(stats + PIXIE_STAT_KERNEL, 1ull);
+            count_launch();
+        }
     }
-    PX_CUDA(launch_codebook_prep(W, K, C, plan, ws.wimg, ws.aux, stream));
-    TcParams p{};
-    p.n = n;
-    p.tile_first = tile_first;
-    p.tile_stride = tile_stride;
-    p.ntiles = ntiles;
-    p.wimg = ws.wimg;
-    p.labels = labels;
-    p.compact_labels = compact;
-    p.stats = stats;
-    p.ctl = ws.aux;
-    p.plan = plan;
-    PX_CUDA(launch_bmu_tc(tm, p, num_sms_current_device(), stream));
-    // rows the tensor-core kernel could not settle (NaN/Inf rows, degenerate codebooks): exact
-    // kernel; returns immediately when the counter is zero.
-    PX_CUDA(launch_bmu_exact(X, n, C, ldX, W, K, labels, tile_first, tile_stride, ntiles, compact,
-                             &ws.aux->fixup_count, stream));
-    if (stats) {
-        set_u64_kernel<<<1, 1, 0, stream>>>(stats + PIXIE_STAT_KERNEL, 1ull);
-        count_launch();
-    }
+    if (SN != nullptr && !fused)
+        PX_CUDA(launch_cluster_sums(X, n, C, ldX, labels, compact, K, tile_first, tile_stride,
+                                    ntiles, ws.partials, sum_parts(), SN, ws.aux->sums_sync,
+                                    stream));
     return PIXIE_OK;
 }
 
@@ -228,12 +243,8 @@ int pixie_bmu_f32(const float *X, int64_t n, int32_t C, int64_t ldX, const float
     Workspace ws = carve(workspace, 0, C, K);
     if (!workspace || ws_bytes < ws.total) return PIXIE_ERR_WORKSPACE;
     const int64_t ntiles = (n + kTile - 1) / kTile;
-    int rc = bmu_tiles(X, n, C, ldX, W, K, labels, 0, 0, 1, ntiles, ws, flags, stats_or_null, st);
-    if (rc != PIXIE_OK) return rc;
-    if (SN_or_null)
-        PX_CUDA(launch_cluster_sums(X, n, C, ldX, labels, 0, K, 0, 1, ntiles, ws.partials,
-                                    sum_parts(), SN_or_null, ws.aux->sums_sync, st));
-    return PIXIE_OK;
+    return bmu_tiles(X, n, C, ldX, W, K, labels, 0, 0, 1, ntiles, ws, flags, stats_or_null,
+                     SN_or_null, st);
 }
 
 int pixie_bmu_dist_f64(const float *X, int64_t n, int32_t C, int64_t ldX, const float *W, int32_t K,
@@ -274,12 +285,8 @@ int pixie_som_accum_f32(const float *X, int64_t n, int32_t C, int64_t ldX, const
         tile_first < tiles_total ? (tiles_total - tile_first + tile_stride - 1) / tile_stride : 0;
     Workspace ws = carve(workspace, ntiles * kTile, C, K);
     if (!workspace || ws_bytes < ws.total) return PIXIE_ERR_WORKSPACE;
-    int rc = bmu_tiles(X, n, C, ldX, W32, K, ws.labels_scratch, 1, tile_first, tile_stride, ntiles,
-                       ws, flags, stats_or_null, st);
-    if (rc != PIXIE_OK) return rc;
-    PX_CUDA(launch_cluster_sums(X, n, C, ldX, ws.labels_scratch, 1, K, tile_first, tile_stride,
-                                ntiles, ws.partials, sum_parts(), SN, ws.aux->sums_sync, st));
-    return PIXIE_OK;
+    return bmu_tiles(X, n, C, ldX, W32, K, ws.labels_scratch, 1, tile_first, tile_stride, ntiles,
+                     ws, flags, stats_or_null, SN, st);
 }
 
 int pixie_som_apply_f64(double *W64, float *W32, const double *SN, int32_t xdim, int32_t ydim,

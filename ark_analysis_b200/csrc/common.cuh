@@ -46,10 +46,13 @@ struct TcPlan {
     int nstage;  // X tile pipeline depth (multiple of NG)
     uint32_t stage_bytes, wimg_bytes;
     uint32_t off_ones, off_x, off_bar, off_pairs;
+    uint32_t off_acc, off_lab;  // fused accumulation (train mode): NG x K x (C+1) fp32, NG x 128 int
+    int acc;                    // 1 = this plan has room for the fused accumulation
     uint32_t smem_bytes;  // dynamic shared memory to request (includes 1 KiB alignment slack)
 };
 
-TcPlan make_tc_plan(int C, int K);
+// acc = true: also reserve per-group fp32 accumulators for the fused per-node sums (train mode)
+TcPlan make_tc_plan(int C, int K, bool acc = false);
 
 struct TcParams {
     int64_t n;             // rows of X
@@ -61,6 +64,10 @@ struct TcParams {
     int compact_labels;
     unsigned long long *stats;  // may be null
     CodebookAux *ctl;           // fixup_count lives here
+    // fused per-node sums (null = plain assignment): per-CTA partials [grid][K][C+1] fp32, folded
+    // into SN [K][C+1] fp64 behind a grid barrier on ctl->sums_sync
+    float *partials;
+    double *SN;
     TcPlan plan;
 };
 
@@ -72,7 +79,7 @@ cudaError_t launch_bmu_tc(const CUtensorMap &tmX, const TcParams &p, int num_sms
 cudaError_t launch_bmu_exact(const float *X, int64_t n, int C, int64_t ldX, const float *W, int K,
                              int32_t *labels, int64_t tile_first, int64_t tile_stride,
                              int64_t ntiles, int compact_labels, const int *fixup_count_or_null,
-                             cudaStream_t stream);
+                             double *SN_add_or_null, cudaStream_t stream);
 cudaError_t launch_bmu_dist(const float *X, int64_t n, int C, int64_t ldX, const float *W, int K,
                             const int32_t *labels, double *dists, cudaStream_t stream);
 cudaError_t launch_cluster_sums(const float *X, int64_t n, int C, int64_t ldX,

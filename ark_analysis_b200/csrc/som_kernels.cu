@@ -23,7 +23,7 @@ __global__ void __launch_bounds__(128)
 bmu_exact_kernel(const float *__restrict__ X, int64_t n, int C, int64_t ldX,
                  const float *__restrict__ W, int K, int32_t *__restrict__ labels,
                  int64_t tile_first, int64_t tile_stride, int64_t ntiles, int compact_labels,
-                 const int *__restrict__ fixup_count)
+                 const int *__restrict__ fixup_count, double *__restrict__ SN_add)
 {
     const bool fix_only = fixup_count != nullptr;
     if (fix_only && *fixup_count == 0) return;  // nothing was flagged: the common case
@@ -67,6 +67,12 @@ bmu_exact_kernel(const float *__restrict__ X, int64_t n, int C, int64_t ldX,
                 }
             }
             if (lane == src) labels[lidx] = (bid == 0x7fffffff) ? 0 : bid + 1;
+            if (SN_add != nullptr && bid != 0x7fffffff) {
+                // train mode: the tensor-core kernel left this row out of the fused sums
+                double *dst = SN_add + (size_t)bid * (C + 1);
+                for (int c = lane; c < C; c += 32) atomicAdd(dst + c, (double)__ldg(x + c));
+                if (lane == 0) atomicAdd(dst + C, 1.0);
+            }
         }
     }
 }
@@ -74,13 +80,13 @@ bmu_exact_kernel(const float *__restrict__ X, int64_t n, int C, int64_t ldX,
 cudaError_t launch_bmu_exact(const float *X, int64_t n, int C, int64_t ldX, const float *W, int K,
                              int32_t *labels, int64_t tile_first, int64_t tile_stride,
                              int64_t ntiles, int compact_labels, const int *fixup_count_or_null,
-                             cudaStream_t stream)
+                             double *SN_add_or_null, cudaStream_t stream)
 {
     if (ntiles <= 0) return cudaSuccess;
     int64_t grid = ntiles < 148 * 16 ? ntiles : 148 * 16;
     bmu_exact_kernel<<<(unsigned)grid, 128, 0, stream>>>(X, n, C, ldX, W, K, labels, tile_first,
                                                         tile_stride, ntiles, compact_labels,
-                                                        fixup_count_or_null);
+                                                        fixup_count_or_null, SN_add_or_null);
     count_launch();
     return cudaGetLastError();
 }
