@@ -772,10 +772,17 @@ bmu_tc_kernel(const __grid_constant__ CUtensorMap tmX, const TcParams p)
             const int rounds = (per + nthr / 8 - 1) / (nthr / 8);  // uniform trip count
             for (int it = 0; it < rounds; ++it) {
                 const int e = e0 + it * (nthr / 8) + oct;
+                // all loads of this thread first (independent, in flight together), then the sum
+                // in ascending CTA order
+                float v[kFoldMax];
+#pragma unroll
+                for (int u = 0; u < kFoldMax; ++u) {
+                    const int pp = q + 8 * u;
+                    v[u] = (e < e1 && pp < nparts) ? __ldcg(p.partials + (size_t)pp * len + e) : 0.f;
+                }
                 double acc = 0.0;
-                if (e < e1)
-                    for (int pp = q; pp < nparts; pp += 8)
-                        acc += (double)__ldcg(p.partials + (size_t)pp * len + e);
+#pragma unroll
+                for (int u = 0; u < kFoldMax; ++u) acc += (double)v[u];
                 acc += __shfl_xor_sync(0xffffffffu, acc, 1);
                 acc += __shfl_xor_sync(0xffffffffu, acc, 2);
                 acc += __shfl_xor_sync(0xffffffffu, acc, 4);

@@ -1,6 +1,7 @@
 // capi.cu -- the extern "C" surface declared in include/pixie_b200.h.
 #include <float.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <atomic>
@@ -299,6 +300,61 @@ int pixie_som_apply_f64(double *W64, float *W32, const double *SN, int32_t xdim,
     return PIXIE_OK;
 }
 
+// Enqueues the T = rlen * B accumulate + apply steps on `st` (no host synchronisation).
+static int enqueue_train_steps(const float *X, int64_t n, int32_t C, int64_t ldX, double *W64,
+                               float *W32, double *SN, int32_t xdim, int32_t ydim, int32_t rlen,
+                               int32_t batches_per_pass, double alpha0, double alpha1,
+                               double radius0, double radius1, void *workspace, size_t ws_bytes,
+                               uint32_t flags, cudaStream_t st)
+{
+    const int K = xdim * ydim;
+    const int64_t T = (int64_t)rlen * batches_per_pass;
+    // W32 = fp32(W64) for the first step: an apply with nothing accumulated (SN = 0) only casts
+    PX_CUDA(cudaMemsetAsync(SN, 0, sizeof(double) * (size_t)K * (C + 1), st));
+    int rc = pixie_som_apply_f64(W64, W32, SN, xdim, ydim, C, 1.0, 0.0, st);
+    if (rc != PIXIE_OK) return rc;
+    for (int64_t t = 0; t < T; ++t) {
+        const int64_t m = t % batches_per_pass;
+        rc = pixie_som_accum_f32(X, n, C, ldX, W32, K, m, batches_per_pass, SN, workspace, ws_bytes,
+                                 flags, nullptr, st);
+        if (rc != PIXIE_OK) return rc;
+        const double frac = (double)t / (double)T;
+        const double r = radius0 - (radius0 - radius1) * frac;
+        const double r_eff = r < 1.0 ? 0.5 : r;
+        const double alpha = alpha0 - (alpha0 - alpha1) * frac;
+        rc = pixie_som_apply_f64(W64, W32, SN, xdim, ydim, C, 0.5 * r_eff, alpha, st);
+        if (rc != PIXIE_OK) return rc;
+    }
+    return PIXIE_OK;
+}
+
+namespace {
+// The training pass is ~7 short launches per step; on the host that is launch-bound.  The whole
+// pass is therefore captured once into a CUDA graph (on a private stream: the caller's may be the
+// legacy default stream, which cannot be captured) and replayed on the caller's stream.  Executable
+// graphs are cached on the full argument tuple.
+struct TrainKey {
+    const void *X, *W64, *W32, *SN, *ws;
+    int64_t n, ldX;
+    size_t ws_bytes;
+    int32_t C, xdim, ydim, rlen, B;
+    double a0, a1, r0, r1;
+    uint32_t flags;
+    int device;
+    bool operator==(const TrainKey &o) const { return memcmp(this, &o, sizeof(TrainKey)) == 0; }
+};
+struct TrainGraph {
+    TrainKey key;
+    cudaGraphExec_t exec;
+    unsigned long long launches;  // kernels one replay launches
+    uint64_t stamp;
+};
+std::mutex g_graph_mutex;
+std::vector<TrainGraph> g_graphs;
+uint64_t g_graph_clock = 0;
+cudaStream_t g_capture_stream[64] = {};
+}  // namespace
+
 int pixie_som_train_f32(const float *X, int64_t n, int32_t C, int64_t ldX, double *W64, float *W32,
                         double *SN, int32_t xdim, int32_t ydim, int32_t rlen,
                         int32_t batches_per_pass, double alpha0, double alpha1, double radius0,
@@ -309,24 +365,70 @@ int pixie_som_train_f32(const float *X, int64_t n, int32_t C, int64_t ldX, doubl
         return PIXIE_ERR_INVALID_ARG;
     const int K = xdim * ydim;
     if (bad_shape(n, C, ldX, K) || (n > 0 && !X)) return PIXIE_ERR_INVALID_ARG;
-    const int64_t T = (int64_t)rlen * batches_per_pass;
-    // W32 = fp32(W64) for the first step: an apply with nothing accumulated (SN = 0) only casts
     cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
-    PX_CUDA(cudaMemsetAsync(SN, 0, sizeof(double) * (size_t)K * (C + 1), st));
-    int rc = pixie_som_apply_f64(W64, W32, SN, xdim, ydim, C, 1.0, 0.0, stream);
-    if (rc != PIXIE_OK) return rc;
-    for (int64_t t = 0; t < T; ++t) {
-        const int64_t m = t % batches_per_pass;
-        rc = pixie_som_accum_f32(X, n, C, ldX, W32, K, m, batches_per_pass, SN, workspace, ws_bytes,
-                                 flags, nullptr, stream);
-        if (rc != PIXIE_OK) return rc;
-        const double frac = (double)t / (double)T;
-        const double r = radius0 - (radius0 - radius1) * frac;
-        const double r_eff = r < 1.0 ? 0.5 : r;
-        const double alpha = alpha0 - (alpha0 - alpha1) * frac;
-        rc = pixie_som_apply_f64(W64, W32, SN, xdim, ydim, C, 0.5 * r_eff, alpha, stream);
-        if (rc != PIXIE_OK) return rc;
+
+    cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
+    if (st != nullptr && st != cudaStreamLegacy && st != cudaStreamPerThread)
+        cudaStreamIsCapturing(st, &cap);
+    const char *env = getenv("PIXIE_DISABLE_GRAPH");
+    int dev = 0;
+    PX_CUDA(cudaGetDevice(&dev));
+    if ((env && env[0] == '1') || cap != cudaStreamCaptureStatusNone || dev < 0 || dev >= 64)
+        return enqueue_train_steps(X, n, C, ldX, W64, W32, SN, xdim, ydim, rlen, batches_per_pass,
+                                   alpha0, alpha1, radius0, radius1, workspace, ws_bytes, flags, st);
+
+    TrainKey key;
+    memset(&key, 0, sizeof(key));
+    key.X = X; key.W64 = W64; key.W32 = W32; key.SN = SN; key.ws = workspace;
+    key.n = n; key.ldX = ldX; key.ws_bytes = ws_bytes;
+    key.C = C; key.xdim = xdim; key.ydim = ydim; key.rlen = rlen; key.B = batches_per_pass;
+    key.a0 = alpha0; key.a1 = alpha1; key.r0 = radius0; key.r1 = radius1;
+    key.flags = flags; key.device = dev;
+
+    std::lock_guard<std::mutex> lock(g_graph_mutex);
+    for (auto &g : g_graphs)
+        if (g.key == key) {
+            g.stamp = ++g_graph_clock;
+            PX_CUDA(cudaGraphLaunch(g.exec, st));
+            count_launch((int)g.launches);
+            return PIXIE_OK;
+        }
+    if (!g_capture_stream[dev])
+        PX_CUDA(cudaStreamCreateWithFlags(&g_capture_stream[dev], cudaStreamNonBlocking));
+    cudaStream_t cs = g_capture_stream[dev];
+    const unsigned long long before = pixie::g_launches.load();
+    PX_CUDA(cudaStreamBeginCapture(cs, cudaStreamCaptureModeRelaxed));
+    int rc = enqueue_train_steps(X, n, C, ldX, W64, W32, SN, xdim, ydim, rlen, batches_per_pass,
+                                 alpha0, alpha1, radius0, radius1, workspace, ws_bytes, flags, cs);
+    cudaGraph_t graph = nullptr;
+    cudaError_t e = cudaStreamEndCapture(cs, &graph);
+    const unsigned long long per_replay = pixie::g_launches.load() - before;
+    pixie::g_launches.fetch_sub(per_replay);  // nothing ran during capture
+    if (rc != PIXIE_OK) {
+        if (graph) cudaGraphDestroy(graph);
+        return rc;
     }
+    if (e != cudaSuccess) {
+        set_last_cuda_error(e, "cudaStreamEndCapture");
+        return PIXIE_ERR_CUDA;
+    }
+    cudaGraphExec_t exec = nullptr;
+    e = cudaGraphInstantiate(&exec, graph, 0);
+    cudaGraphDestroy(graph);
+    if (e != cudaSuccess) {
+        set_last_cuda_error(e, "cudaGraphInstantiate");
+        return PIXIE_ERR_CUDA;
+    }
+    if (g_graphs.size() >= 8) {  // evict the least recently used
+        size_t victim = 0;
+        for (size_t i = 1; i < g_graphs.size(); ++i)
+            if (g_graphs[i].stamp < g_graphs[victim].stamp) victim = i;
+        cudaGraphExecDestroy(g_graphs[victim].exec);
+        g_graphs.erase(g_graphs.begin() + victim);
+    }
+    g_graphs.push_back(TrainGraph{key, exec, per_replay, ++g_graph_clock});
+    PX_CUDA(cudaGraphLaunch(exec, st));
+    count_launch((int)per_replay);
     return PIXIE_OK;
 }
 

@@ -95,5 +95,7 @@ void count_launch(int n = 1);
 
 // number of per-CTA partial buffers the cluster-sums kernel uses
 constexpr int kSumParts = 148;
+// partials folded per thread of an octet: ceil(kSumParts / 8)
+constexpr int kFoldMax = (kSumParts + 7) / 8;
 
 }  // namespace pixie

@@ -292,9 +292,17 @@ cluster_sums_kernel(const float *__restrict__ X, int64_t n, int C, int64_t ldX,
         const int rounds = (per + kSumThreads / 8 - 1) / (kSumThreads / 8);  // uniform trip count
         for (int it = 0; it < rounds; ++it) {
             const int e = e0 + it * (kSumThreads / 8) + oct;
+            // all loads of this thread first (independent, in flight together), then the sum in
+            // ascending CTA order
+            float v[kFoldMax];
+#pragma unroll
+            for (int u = 0; u < kFoldMax; ++u) {
+                const int p = q + 8 * u;
+                v[u] = (e < e1 && p < nparts) ? __ldcg(partials + (size_t)p * len + e) : 0.f;
+            }
             double a = 0.0;
-            if (e < e1)
-                for (int p = q; p < nparts; p += 8) a += (double)__ldcg(partials + (size_t)p * len + e);
+#pragma unroll
+            for (int u = 0; u < kFoldMax; ++u) a += (double)v[u];
             a += __shfl_xor_sync(0xffffffffu, a, 1);
             a += __shfl_xor_sync(0xffffffffu, a, 2);
             a += __shfl_xor_sync(0xffffffffu, a, 4);
