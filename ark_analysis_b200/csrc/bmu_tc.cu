@@ -272,7 +272,7 @@ __device__ __noinline__ double pair_dist_f64(const uint8_t *xs, const uint8_t *w
 // ------------------------------------------------------------------------------------------------
 // the kernel
 // ------------------------------------------------------------------------------------------------
-template <int SL, int SPC, int NCH, int NG>
+template <int SL, int SPC, int NCH, int NG, bool ACC>
 __global__ void __launch_bounds__(NG * 128 + 64, 1)
 bmu_tc_kernel(const __grid_constant__ CUtensorMap tmX, const TcParams p)
 {
@@ -328,7 +328,7 @@ bmu_tc_kernel(const __grid_constant__ CUtensorMap tmX, const TcParams p)
         tmem_relinquish();
     }
     for (int i = threadIdx.x; i < 1024; i += blockDim.x) reinterpret_cast<float *>(ones)[i] = 1.0f;
-    if (p.partials != nullptr) {
+    if constexpr (ACC) {
         float *a = reinterpret_cast<float *>(smem + pl.off_acc);
         for (int i = threadIdx.x; i < NG * pl.K * (pl.C + 1); i += blockDim.x) a[i] = 0.f;
     }
@@ -421,7 +421,7 @@ bmu_tc_kernel(const __grid_constant__ CUtensorMap tmX, const TcParams p)
         const float wmax2 = wmax * wmax;
         const bool w_nonneg = p.ctl->w_has_negative == 0;
         // fused accumulation (train mode)
-        const bool do_acc = p.partials != nullptr;
+        constexpr bool do_acc = ACC;
         const int acc_ld = pl.C + 1;
         const int acc_cq = (pl.C + 1 + 3) / 4;  // columns per warp of the group (<= 32)
         float *acc_tab = reinterpret_cast<float *>(smem + pl.off_acc) + (size_t)g * pl.K * acc_ld;
@@ -671,7 +671,7 @@ bmu_tc_kernel(const __grid_constant__ CUtensorMap tmX, const TcParams p)
             } else if (p.compact_labels) {
                 *lab_ptr = 0;  // padding row of the last tile: never counted
             }
-            if (do_acc) {
+            if constexpr (do_acc) {
                 // ---- fused per-node sums: the group's 4 warps split the C+1 columns (channels +
                 // count); each warp walks the tile's 128 rows IN ROW ORDER with plain
                 // read-modify-writes on the group's private table (no atomics: a column belongs to
@@ -736,7 +736,7 @@ bmu_tc_kernel(const __grid_constant__ CUtensorMap tmX, const TcParams p)
         tc_fence_after();
         tmem_dealloc(tmem_base, (uint32_t)pl.tmem_cols);
     }
-    if (p.partials != nullptr) {
+    if constexpr (ACC) {
         // ---- fused sums, part 2: groups are combined in group order into this CTA's partial,
         // then (grid barrier; every CTA is resident: grid <= SM count, one CTA per SM) each CTA
         // folds its slice of the table over all partials in CTA order, in fp64.
@@ -800,17 +800,25 @@ bmu_tc_kernel(const __grid_constant__ CUtensorMap tmX, const TcParams p)
     }
 }
 
+template <int SL, int SPC, int NCH, int NG, bool ACC>
+static cudaError_t launch_acc(const CUtensorMap &tmX, const TcParams &p, int grid,
+                              cudaStream_t stream)
+{
+    cudaError_t e = cudaFuncSetAttribute(bmu_tc_kernel<SL, SPC, NCH, NG, ACC>,
+                                         cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         (int)p.plan.smem_bytes);
+    if (e != cudaSuccess) return e;
+    bmu_tc_kernel<SL, SPC, NCH, NG, ACC><<<grid, NG * 128 + 64, p.plan.smem_bytes, stream>>>(tmX, p);
+    count_launch();
+    return cudaGetLastError();
+}
+
 template <int SL, int SPC, int NCH, int NG>
 static cudaError_t launch_one(const CUtensorMap &tmX, const TcParams &p, int grid,
                               cudaStream_t stream)
 {
-    cudaError_t e = cudaFuncSetAttribute(bmu_tc_kernel<SL, SPC, NCH, NG>,
-                                         cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                         (int)p.plan.smem_bytes);
-    if (e != cudaSuccess) return e;
-    bmu_tc_kernel<SL, SPC, NCH, NG><<<grid, NG * 128 + 64, p.plan.smem_bytes, stream>>>(tmX, p);
-    count_launch();
-    return cudaGetLastError();
+    if (p.partials != nullptr) return launch_acc<SL, SPC, NCH, NG, true>(tmX, p, grid, stream);
+    return launch_acc<SL, SPC, NCH, NG, false>(tmX, p, grid, stream);
 }
 
 cudaError_t launch_bmu_tc(const CUtensorMap &tmX, const TcParams &p, int num_sms,
