@@ -89,7 +89,8 @@ TcPlan make_tc_plan(int C, int K, bool acc)
             acc ? ((uint32_t)v.NG * (uint32_t)K * (uint32_t)(C + 1) * 4u + 15u) / 16u * 16u +
                       (uint32_t)v.NG * 512u
                 : 0u;
-        const uint32_t scratch = 256u + (uint32_t)(4 * v.NG) * kWarpPairCap * 8u + acc_bytes;
+        const uint32_t pair_cap = acc ? kWarpPairCapAcc : kWarpPairCap;
+        const uint32_t scratch = 256u + (uint32_t)(4 * v.NG) * pair_cap * 8u + acc_bytes;
         const uint32_t limit = 227u * 1024u - 1024u;
         if (p.off_x + scratch + (uint32_t)v.NG * p.stage_bytes > limit) continue;
         p.nstage = (int)((limit - p.off_x - scratch) / p.stage_bytes);
@@ -99,7 +100,8 @@ TcPlan make_tc_plan(int C, int K, bool acc)
         p.nstage = p.nstage / v.NG * v.NG;
         p.off_bar = p.off_x + (uint32_t)p.nstage * p.stage_bytes;
         p.off_pairs = p.off_bar + 256u;
-        p.off_acc = p.off_pairs + (uint32_t)(4 * v.NG) * kWarpPairCap * 8u;
+        p.pair_cap = (int)pair_cap;
+        p.off_acc = p.off_pairs + (uint32_t)(4 * v.NG) * pair_cap * 8u;
         p.off_lab = p.off_acc + (acc_bytes ? acc_bytes - (uint32_t)v.NG * 512u : 0u);
         p.acc = acc ? 1 : 0;
         p.smem_bytes = p.off_acc + acc_bytes + 1024u;
@@ -269,6 +271,206 @@ __device__ __noinline__ double pair_dist_f64(const uint8_t *xs, const uint8_t *w
     return __dsqrt_rn(acc);
 }
 
+// Grid-wide barrier for the persistent kernel (every CTA is resident: grid <= SM count and one CTA
+// per SM fits).  `counter` only ever grows during a launch; `target` is the value it reaches when
+// all CTAs have arrived at this barrier instance.
+__device__ __forceinline__ void grid_barrier(unsigned int *counter, unsigned int target)
+{
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        atomicAdd(counter, 1u);
+        unsigned spins = 0;
+        while (*reinterpret_cast<volatile unsigned int *>(counter) < target) {
+            __nanosleep(32);
+            if (++spins > (1u << 25)) __trap();  // seconds: never on a healthy launch
+        }
+        __threadfence();
+    }
+    __syncthreads();
+}
+
+// tiles of one mini-batch step that this shard holds: local tiles first, first + B, ... whose
+// GLOBAL index (local + tile_offset) is congruent to m mod B
+struct StepTiles {
+    int64_t first, stride, count;
+};
+__device__ __forceinline__ StepTiles step_tiles(const TcParams &p, int st)
+{
+    StepTiles r;
+    if (p.nsteps <= 1 && !p.apply) {
+        r.first = p.tile_first;
+        r.stride = p.tile_stride;
+        r.count = p.ntiles;
+        return r;
+    }
+    const int64_t B = p.B;
+    const int64_t m = (int64_t)(p.t0 + st) % B;
+    r.first = ((m - p.tile_offset) % B + B) % B;
+    r.stride = B;
+    r.count = r.first < p.tiles_total ? (p.tiles_total - r.first + B - 1) / B : 0;
+    return r;
+}
+
+// ------------------------------------------------------------------------------------------------
+// whole-pass mode, end of a step: fold the CTAs' sums, apply the batch update (DESIGN.md section 4,
+// same arithmetic as som_apply_kernel) and rewrite the codebook image for the next step.
+// Called by every thread of every CTA; three grid barriers.
+// ------------------------------------------------------------------------------------------------
+template <int NG>
+__device__ __noinline__ void step_update(const TcParams &p, int st, uint8_t *smem,
+                                         unsigned int &gb_target)
+{
+    const TcPlan &pl = p.plan;
+    const int K = pl.K, C = pl.C, len = K * (C + 1);
+    const int tid = threadIdx.x, nthr = blockDim.x;
+    float *acc = reinterpret_cast<float *>(smem + pl.off_acc);
+    unsigned int *gsync = &p.ctl->grid_sync;
+    const bool timing = blockIdx.x == 0 && tid == 0;
+    uint64_t tm = timing ? global_timer_ns() : 0;
+    auto lap = [&](int slot) {
+        if (timing) {
+            const uint64_t now = global_timer_ns();
+            p.ctl->phase_ns[slot] += now - tm;
+            tm = now;
+        }
+    };
+
+    // 1. groups -> this CTA's partial (group order), accumulators cleared for the next step
+    float *mine = p.partials + (size_t)blockIdx.x * len;
+    for (int i = tid; i < len; i += nthr) {
+        float v = acc[i];
+        acc[i] = 0.f;
+#pragma unroll
+        for (int gg = 1; gg < NG; ++gg) {
+            v += acc[gg * len + i];
+            acc[gg * len + i] = 0.f;
+        }
+        mine[i] = v;
+    }
+    gb_target += gridDim.x;
+    grid_barrier(gsync, gb_target);
+    lap(1);
+
+    // 2. every CTA folds its slice of the table over all partials, CTA order, fp64
+    {
+        const int nparts = gridDim.x;
+        const int per = (len + nparts - 1) / nparts;
+        const int e0 = blockIdx.x * per;
+        const int e1 = min(len, e0 + per);
+        const int oct = tid >> 3, q = tid & 7;
+        const int rounds = (per + nthr / 8 - 1) / (nthr / 8);  // uniform trip count
+        for (int it = 0; it < rounds; ++it) {
+            const int e = e0 + it * (nthr / 8) + oct;
+            float v[kFoldMax];
+#pragma unroll
+            for (int u = 0; u < kFoldMax; ++u) {
+                const int pp = q + 8 * u;
+                v[u] = (e < e1 && pp < nparts) ? __ldcg(p.partials + (size_t)pp * len + e) : 0.f;
+            }
+            double a = 0.0;
+#pragma unroll
+            for (int u = 0; u < kFoldMax; ++u) a += (double)v[u];
+            a += __shfl_xor_sync(0xffffffffu, a, 1);
+            a += __shfl_xor_sync(0xffffffffu, a, 2);
+            a += __shfl_xor_sync(0xffffffffu, a, 4);
+            if (e < e1 && q == 0) p.SN[e] = a;
+        }
+    }
+    if (blockIdx.x == 0 && tid == 0) {
+        // slot the update below publishes the next step's norms into
+        p.ctl->pp_wmax_bits[(st + 1) & 1] = 0;
+        p.ctl->pp_w_has_negative[(st + 1) & 1] = 0;
+    }
+    lap(2);
+    gb_target += gridDim.x;
+    grid_barrier(gsync, gb_target);
+    lap(3);
+
+    // 3. batch update of node k by CTA k (k < K); schedule of step t = t0 + st of T
+    {
+        const double frac = (double)(p.t0 + st) / (double)p.T;
+        const double r = p.r0 - (p.r0 - p.r1) * frac;
+        const double r_eff = r < 1.0 ? 0.5 : r;
+        const double sigma = 0.5 * r_eff;
+        const double inv2s2 = 1.0 / (2.0 * sigma * sigma);
+        const double alpha = p.a0 - (p.a0 - p.a1) * frac;
+        // the folded table, staged once per CTA in the (idle, already cleared) accumulator area
+        double *s_sn = reinterpret_cast<double *>(acc);
+        if ((int)blockIdx.x < K)
+            for (int i = tid; i < len; i += nthr) s_sn[i] = __ldcg(p.SN + i);
+        __syncthreads();
+        double *s_h = reinterpret_cast<double *>(smem + pl.off_pairs);  // [K], pair lists are idle
+        double *s_cnt = s_h + K;                                        // [K]
+        double *s_red = s_cnt + K;                                      // [32] block reduction
+        int *s_flag = reinterpret_cast<int *>(s_red + 32);
+        const int ydim = p.ydim;
+        for (int k = blockIdx.x; k < K; k += gridDim.x) {
+            const int kx = k / ydim, ky = k % ydim;
+            for (int b = tid; b < K; b += nthr) {
+                const int dx = abs(kx - b / ydim), dy = abs(ky - b % ydim);
+                const double d = (double)(dx > dy ? dx : dy);
+                const double cnt = s_sn[(size_t)b * (C + 1) + C];
+                s_cnt[b] = cnt;
+                s_h[b] = cnt == 0.0 ? 0.0 : exp(-d * d * inv2s2);
+            }
+            if (tid == 0) *s_flag = 0;
+            __syncthreads();
+            double den = 0.0;
+            for (int b = 0; b < K; ++b) den += s_h[b] * s_cnt[b];
+            const double beta = den > 0.0 ? 1.0 - pow(1.0 - alpha, den) : 0.0;
+            double nrm2 = 0.0;
+            bool neg = false;
+            char *img = reinterpret_cast<char *>(p.wimg_rw);
+            for (int c = tid; c < C; c += nthr) {
+                double w = p.W64[(size_t)k * C + c];
+                if (den > 0.0) {
+                    double num = 0.0;
+                    for (int b = 0; b < K; ++b) num += s_h[b] * s_sn[(size_t)b * (C + 1) + c];
+                    w += beta * (num / den - w);
+                    p.W64[(size_t)k * C + c] = w;
+                }
+                const float wf = (float)w;
+                p.W32[(size_t)k * C + c] = wf;
+                *reinterpret_cast<float *>(img + img_offset(pl.Ntot, k, c)) = -2.0f * wf;
+                nrm2 += (double)wf * (double)wf;
+                if (__float_as_int(wf) < 0) neg = true;
+            }
+            // block reduction of ||w_k||^2 (only the first C threads contribute)
+            for (int o = 16; o > 0; o >>= 1) nrm2 += __shfl_xor_sync(0xffffffffu, nrm2, o);
+            if (neg) atomicOr(s_flag, 1);
+            if ((tid & 31) == 0 && (tid >> 5) < 32) s_red[tid >> 5] = nrm2;
+            __syncthreads();
+            if (tid == 0) {
+                double tot = 0.0;
+                for (int w = 0; w < (nthr + 31) / 32 && w < 32; ++w) tot += s_red[w];
+                float bias = (float)tot;
+                if (!(bias <= FLT_MAX)) bias = FLT_MAX;
+                const float h = __uint_as_float(__float_as_uint(bias) & 0xFFFFE000u);
+                const float r1 = bias - h;
+                const float m = __uint_as_float(__float_as_uint(r1) & 0xFFFFE000u);
+                const float l = r1 - m;
+                *reinterpret_cast<float *>(img + img_offset(pl.Ntot, k, pl.C8 + 0)) = h;
+                *reinterpret_cast<float *>(img + img_offset(pl.Ntot, k, pl.C8 + 1)) = m;
+                *reinterpret_cast<float *>(img + img_offset(pl.Ntot, k, pl.C8 + 2)) = l;
+                float nr = (float)sqrt(tot) * 1.0000005f;
+                if (!(nr <= FLT_MAX)) nr = FLT_MAX;
+                atomicMax(&p.ctl->pp_wmax_bits[(st + 1) & 1], __float_as_int(nr));
+                if (*s_flag) atomicOr(&p.ctl->pp_w_has_negative[(st + 1) & 1], 1);
+            }
+            __syncthreads();
+        }
+    }
+    // the staged table sat in the accumulator area: clear it again for the next step
+    if ((int)blockIdx.x < K)
+        for (int i = tid; i < (len * 2 + 1); i += nthr)
+            if (i < NG * len) acc[i] = 0.f;
+    lap(4);
+    gb_target += gridDim.x;
+    grid_barrier(gsync, gb_target);
+    lap(5);
+}
+
 // ------------------------------------------------------------------------------------------------
 // the kernel
 // ------------------------------------------------------------------------------------------------
@@ -307,7 +509,7 @@ bmu_tc_kernel(const __grid_constant__ CUtensorMap tmX, const TcParams p)
         reinterpret_cast<volatile uint32_t *>(smem + pl.off_bar + 16u * kMaxStages + 72u);
 
     const int nstage = pl.nstage;
-    const int64_t ntiles = p.ntiles;
+    const int nsteps = p.nsteps > 1 ? p.nsteps : 1;
 
     // ---------------------------------------------------------------- one-time setup
     if (warp == NEPI && lane == 0) {
@@ -338,29 +540,42 @@ bmu_tc_kernel(const __grid_constant__ CUtensorMap tmX, const TcParams p)
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
 
+    // Every role walks the same sequence: step st = 0..nsteps-1, within a step this CTA's tiles
+    // it = 0..cnt-1 (tile j = blockIdx.x + it * gridDim.x of the step).  `seq` numbers the CTA's tiles
+    // across ALL steps; it fixes the pipeline slot of a tile: X stage seq % nstage, epilogue group
+    // seq % NG, accumulator use seq / NG -- so barrier phases simply keep running across steps.
+    uint32_t base_seq = 0;
+    unsigned int gb_target = 0;
+    uint32_t st_flag = 0, st_pairs = 0, st_fp64 = 0, st_fix = 0;  // per-thread statistics
+    uint64_t step_t0 = (ACC && blockIdx.x == 0 && threadIdx.x == 0) ? global_timer_ns() : 0;  // grid-barrier instances passed so far x gridDim.x
+    for (int st = 0; st < nsteps; ++st) {
+    const StepTiles stp = step_tiles(p, st);
+    const int64_t ntiles = stp.count;
+    const uint32_t cnt =
+        (int64_t)blockIdx.x < ntiles ? (uint32_t)((ntiles - blockIdx.x + gridDim.x - 1) / gridDim.x) : 0u;
+
     if (warp == NEPI) {
         // ============================================================ TMA producer
         if (lane == 0) {
-            // codebook image: linear bulk copies (image is pre-swizzled in global memory)
+            // codebook image: linear bulk copies (image is pre-swizzled in global memory); in
+            // whole-pass mode it was rewritten by other CTAs through the generic proxy
+            asm volatile("fence.proxy.async;" ::: "memory");
             mbar_arrive_expect_tx(bar_w, pl.wimg_bytes);
             for (uint32_t off = 0; off < pl.wimg_bytes; off += 16384u) {
                 const uint32_t sz = min(16384u, pl.wimg_bytes - off);
                 bulk_load(sbase + off, reinterpret_cast<const uint8_t *>(p.wimg) + off, sz, bar_w);
             }
-            int s = 0;
-            uint32_t ph = 0;
-            for (int64_t j = blockIdx.x; j < ntiles; j += gridDim.x) {
+            uint32_t s = base_seq % (uint32_t)nstage;          // one division per step, then
+            uint32_t ph = (base_seq / (uint32_t)nstage) & 1u;  // incremental
+            for (uint32_t it = 0; it < cnt; ++it, ph ^= (++s == (uint32_t)nstage), s = s == (uint32_t)nstage ? 0u : s) {
                 mbar_wait(bar_empty + 8u * s, ph ^ 1u);
                 mbar_arrive_expect_tx(bar_full + 8u * s, pl.stage_bytes);
-                const int64_t tile = p.tile_first + j * p.tile_stride;
+                const int64_t j = (int64_t)blockIdx.x + (int64_t)it * gridDim.x;
+                const int64_t tile = stp.first + j * stp.stride;
                 const int32_t row0 = (int32_t)(tile * kTile);
                 for (int b = 0; b < pl.nblkX; ++b)
-                    tma_load_2d(sbase + pl.off_x + (uint32_t)s * pl.stage_bytes + (uint32_t)b * 16384u,
+                    tma_load_2d(sbase + pl.off_x + s * pl.stage_bytes + (uint32_t)b * 16384u,
                                 &tmX, bar_full + 8u * s, b * 32, row0, kEvictFirst);
-                if (++s == nstage) {
-                    s = 0;
-                    ph ^= 1u;
-                }
             }
         }
     } else if (warp == NEPI + 1) {
@@ -371,15 +586,16 @@ bmu_tc_kernel(const __grid_constant__ CUtensorMap tmX, const TcParams p)
             // bias K-step: columns C8..C8+7 of the codebook image
             const uint32_t bias_blk = (uint32_t)(pl.C8 >> 5), bias_off = (uint32_t)(pl.C8 & 31) * 4u;
             const uint32_t wblk_bytes = (uint32_t)((NCH - 1) * NCHUNK + NMMA) * 128u;
-            mbar_wait(bar_w, 0);
-            int s = 0;
-            uint32_t ph = 0;
-            uint32_t q = 0;  // accumulator-chunk counter
-            for (int64_t j = blockIdx.x; j < ntiles; j += gridDim.x) {
+            mbar_wait(bar_w, (uint32_t)st & 1u);
+            uint32_t s = base_seq % (uint32_t)nstage;
+            uint32_t ph = (base_seq / (uint32_t)nstage) & 1u;
+            for (uint32_t it = 0; it < cnt; ++it, ph ^= (++s == (uint32_t)nstage), s = s == (uint32_t)nstage ? 0u : s) {
+                const uint32_t seq = base_seq + it;
                 mbar_wait(bar_full + 8u * s, ph);
-                const uint32_t xs_addr = sbase + pl.off_x + (uint32_t)s * pl.stage_bytes;
+                const uint32_t xs_addr = sbase + pl.off_x + s * pl.stage_bytes;
 #pragma unroll
-                for (int c = 0; c < NCH; ++c, ++q) {
+                for (int c = 0; c < NCH; ++c) {
+                    const uint32_t q = seq * (uint32_t)NCH + (uint32_t)c;  // accumulator-chunk counter
                     const uint32_t buf = q % NBUF;
                     const uint32_t bph = (q / NBUF) & 1u;
                     mbar_wait(bar_tempty + 8u * buf, bph ^ 1u);
@@ -397,10 +613,6 @@ bmu_tc_kernel(const __grid_constant__ CUtensorMap tmX, const TcParams p)
                     mma_tf32(d_tmem, desc_ones, dbias, idesc, 1u);
                     mma_commit(bar_tfull + 8u * buf);
                 }
-                if (++s == nstage) {
-                    s = 0;
-                    ph ^= 1u;
-                }
             }
         }
     } else {
@@ -409,17 +621,19 @@ bmu_tc_kernel(const __grid_constant__ CUtensorMap tmX, const TcParams p)
         const int quad = warp & 3;           // TMEM lane quadrant this warp may read
         const int row = quad * 32 + lane;    // tile row == TMEM lane
         const uint32_t r7 = (uint32_t)(row & 7);
-        uint32_t *pairs = reinterpret_cast<uint32_t *>(smem + pl.off_pairs) + warp * (2 * kWarpPairCap);
-        float *d2buf = reinterpret_cast<float *>(pairs + kWarpPairCap);
+        const int pair_cap = pl.pair_cap;
+        uint32_t *pairs = reinterpret_cast<uint32_t *>(smem + pl.off_pairs) + warp * (2 * pair_cap);
+        float *d2buf = reinterpret_cast<float *>(pairs + pair_cap);
         constexpr int Ntot = (NCH - 1) * NCHUNK + NMMA;
         const int nchunks16 = pl.C8 >> 2;    // 16-byte chunks holding real channels
         const float eps32 = (float)(pl.C + 8) * 2.4e-7f;
         const uint32_t tmem_lane = tmem_base + ((uint32_t)(quad * 32) << 16);
-        uint32_t st_flag = 0, st_pairs = 0, st_fp64 = 0, st_fix = 0;
-        mbar_wait(bar_w, 0);  // codebook image visible to this thread (stages 2/3 read it)
-        const float wmax = __int_as_float(p.ctl->wmax_bits);
+        mbar_wait(bar_w, (uint32_t)st & 1u);  // codebook image visible to this thread
+        // norms of the codebook this step runs against: written by the prep kernel for the first
+        // step, by the previous step's in-kernel update (ping-pong slot) afterwards
+        const float wmax = __int_as_float(st == 0 ? p.ctl->wmax_bits : p.ctl->pp_wmax_bits[st & 1]);
         const float wmax2 = wmax * wmax;
-        const bool w_nonneg = p.ctl->w_has_negative == 0;
+        const bool w_nonneg = (st == 0 ? p.ctl->w_has_negative : p.ctl->pp_w_has_negative[st & 1]) == 0;
         // fused accumulation (train mode)
         constexpr bool do_acc = ACC;
         const int acc_ld = pl.C + 1;
@@ -427,17 +641,17 @@ bmu_tc_kernel(const __grid_constant__ CUtensorMap tmX, const TcParams p)
         float *acc_tab = reinterpret_cast<float *>(smem + pl.off_acc) + (size_t)g * pl.K * acc_ld;
         int *acc_lab = reinterpret_cast<int *>(smem + pl.off_lab) + g * kTile;
 
-        // stage / phase bookkeeping of this group's tile sequence (it = g, g+NG, ...)
-        int s = g % nstage;
-        uint32_t ph = (uint32_t)((g / nstage) & 1);
-        uint32_t use = 0;  // how many tiles this group has consumed
-        const int64_t j0 = (int64_t)blockIdx.x + (int64_t)g * gridDim.x;
-        const int64_t jstep = (int64_t)NG * gridDim.x;
-        int64_t grow = (p.tile_first + j0 * p.tile_stride) * kTile + row;  // global row
-        const int64_t grow_step = jstep * p.tile_stride * kTile;
-        int32_t *lab_ptr = p.labels + (p.compact_labels ? j0 * kTile + row : grow);
-        const int64_t lab_step = p.compact_labels ? jstep * kTile : grow_step;
-        for (int64_t j = j0; j < ntiles; j += jstep, ++use, grow += grow_step, lab_ptr += lab_step) {
+        // this group's tiles of the step: local indices it with (base_seq + it) % NG == g
+        const uint32_t it0 = ((uint32_t)g + (uint32_t)NG - base_seq % (uint32_t)NG) % (uint32_t)NG;
+        uint32_t s = (base_seq + it0) % (uint32_t)nstage;          // one division per step, then
+        uint32_t ph = ((base_seq + it0) / (uint32_t)nstage) & 1u;  // incremental (+NG per tile)
+        for (uint32_t it = it0; it < cnt; it += (uint32_t)NG) {
+            const uint32_t seq = base_seq + it;
+            const uint32_t use = seq / (uint32_t)NG;  // NG is a power of two: a shift
+            const int64_t j = (int64_t)blockIdx.x + (int64_t)it * gridDim.x;
+            const int64_t grow = (stp.first + j * stp.stride) * kTile + row;  // global row
+            int32_t *lab_ptr =
+                p.labels ? p.labels + (p.compact_labels ? j * kTile + row : grow) : nullptr;
             const uint8_t *xs = xs0 + (uint32_t)s * pl.stage_bytes;
 
             mbar_wait(bar_full + 8u * s, ph);  // X tile landed
@@ -495,8 +709,8 @@ bmu_tc_kernel(const __grid_constant__ CUtensorMap tmX, const TcParams p)
                     buf = (uint32_t)g;
                     bph = use & 1u;
                 } else {
-                    // chunk counter q = it * 2 + c with it = g + 2 * use; buffers alternate
-                    const uint32_t q = ((uint32_t)g + 2u * use) * 2u + (uint32_t)c;
+                    // chunk counter q = seq * 2 + c; buffers alternate
+                    const uint32_t q = seq * 2u + (uint32_t)c;
                     buf = q & 1u;
                     bph = (q >> 1) & 1u;
                     // Both groups alternate on the same buffer, so this group may get here a whole
@@ -592,10 +806,10 @@ bmu_tc_kernel(const __grid_constant__ CUtensorMap tmX, const TcParams p)
                 const unsigned b3 = __ballot_sync(0xffffffffu, cntf & 8);
                 const int pbase = __popc(b0 & lt) + 2 * __popc(b1 & lt) + 4 * __popc(b2 & lt) +
                                   8 * __popc(b3 & lt);
-                if (flagged && pbase + nc > kWarpPairCap) flagged = false;  // overflow: fix-up
+                if (flagged && pbase + nc > pair_cap) flagged = false;  // overflow: fix-up
                 // slots [0, total) hold every pair that was written (overflowed lanes leave holes)
                 int total = __popc(b0) + 2 * __popc(b1) + 4 * __popc(b2) + 8 * __popc(b3);
-                if (total > kWarpPairCap) total = kWarpPairCap;
+                if (total > pair_cap) total = pair_cap;
                 if (flagged) {
                     int t = pbase;
 #pragma unroll
@@ -662,21 +876,60 @@ bmu_tc_kernel(const __grid_constant__ CUtensorMap tmX, const TcParams p)
                 __syncwarp();  // pair buffers are reused by the next tile
             }
             if (label > pl.K) label = kLabelFixup;  // a padded codebook row can only win on garbage
-            if (grow < p.n) {
-                if (label == kLabelFixup) {
-                    ++st_fix;
-                    atomicAdd(&p.ctl->fixup_count, 1);
+            if constexpr (ACC) {
+                // Train mode resolves the rare rows the three stages could not settle right here
+                // (their sums must be in this step's table): the warp runs the reference loop for
+                // such a row cooperatively, lane l over nodes l, l+32, ...; the lexicographic
+                // (distance, index) minimum over lanes is the first minimum of the sequential loop.
+                unsigned fixm = __ballot_sync(0xffffffffu, label == kLabelFixup && grow < p.n);
+                while (fixm) {
+                    const int src = __ffs(fixm) - 1;
+                    fixm &= fixm - 1;
+                    const int frow = quad * 32 + src;
+                    int minid = 0x7fffffff;
+                    double mind = DBL_MAX;
+                    for (int k = lane; k < pl.K; k += 32) {
+                        const double d = pair_dist_f64(xs, ws, Ntot, pl.C, frow, k);
+                        if (d < mind) {
+                            mind = d;
+                            minid = k;
+                        }
+                    }
+                    for (int o = 16; o > 0; o >>= 1) {
+                        const double od = __shfl_xor_sync(0xffffffffu, mind, o);
+                        const int oi = __shfl_xor_sync(0xffffffffu, minid, o);
+                        if (od < mind || (od == mind && oi < minid)) {
+                            mind = od;
+                            minid = oi;
+                        }
+                    }
+                    if (lane == src) {
+                        label = minid == 0x7fffffff ? 0 : minid + 1;
+                        ++st_fix;
+                    }
                 }
-                *lab_ptr = label;
-            } else if (p.compact_labels) {
-                *lab_ptr = 0;  // padding row of the last tile: never counted
+                if (lab_ptr != nullptr) {
+                    if (grow < p.n)
+                        *lab_ptr = label;
+                    else if (p.compact_labels)
+                        *lab_ptr = 0;  // padding row of the last tile: never counted
+                }
+            } else {
+                if (grow < p.n) {
+                    if (label == kLabelFixup) {
+                        ++st_fix;
+                        atomicAdd(&p.ctl->fixup_count, 1);
+                    }
+                    *lab_ptr = label;
+                } else if (p.compact_labels) {
+                    *lab_ptr = 0;  // padding row of the last tile: never counted
+                }
             }
             if constexpr (do_acc) {
                 // ---- fused per-node sums: the group's 4 warps split the C+1 columns (channels +
                 // count); each warp walks the tile's 128 rows IN ROW ORDER with plain
                 // read-modify-writes on the group's private table (no atomics: a column belongs to
-                // one lane), so the sums are deterministic.  Fix-up rows are added by the exact
-                // kernel afterwards.
+                // one lane), so the sums are deterministic.
                 acc_lab[row] = (grow < p.n && label > 0) ? label - 1 : -1;
                 bar_sync(1u + (uint32_t)g, 128);
                 const int col = quad * acc_cq + lane;  // column of the K x (C+1) table
@@ -687,16 +940,40 @@ bmu_tc_kernel(const __grid_constant__ CUtensorMap tmX, const TcParams p)
                     const uint32_t chunk = (uint32_t)(col & 31) >> 2, within = (uint32_t)(col & 3) * 4u;
                     const uint8_t *xb = xs + blk_off + within;
                     float *tab = acc_tab + col;
-#pragma unroll 4
-                    for (int r = 0; r < kTile; ++r) {
-                        const int lab = acc_lab[r];
-                        if (lab >= 0) {
-                            const float v =
-                                is_cnt ? 1.0f
-                                       : *reinterpret_cast<const float *>(
-                                             xb + (uint32_t)r * 128u + ((chunk ^ ((uint32_t)r & 7u)) << 4));
-                            tab[lab * acc_ld] += v;
+                    // Four rows at a time: their labels are warp-uniform, so rows of the same node
+                    // are first merged in registers (earliest row keeps the sum), which leaves up to
+                    // four read-modify-writes on DISTINCT cells -- independent, hence pipelined,
+                    // instead of a 128-long chain of dependent shared-memory round trips.
+                    for (int r = 0; r < kTile; r += 4) {
+                        const int4 lb = *reinterpret_cast<const int4 *>(acc_lab + r);
+                        int l0 = lb.x, l1 = lb.y, l2 = lb.z, l3 = lb.w;
+                        float v0, v1, v2, v3;
+                        if (is_cnt) {
+                            v0 = v1 = v2 = v3 = 1.0f;
+                        } else {
+                            const uint8_t *xr = xb + (uint32_t)r * 128u;
+                            // rows r..r+3 share r & 4; their swizzle keys are (r & 7) + 0..3
+                            v0 = *reinterpret_cast<const float *>(xr + ((chunk ^ ((uint32_t)(r + 0) & 7u)) << 4));
+                            v1 = *reinterpret_cast<const float *>(xr + 128u + ((chunk ^ ((uint32_t)(r + 1) & 7u)) << 4));
+                            v2 = *reinterpret_cast<const float *>(xr + 256u + ((chunk ^ ((uint32_t)(r + 2) & 7u)) << 4));
+                            v3 = *reinterpret_cast<const float *>(xr + 384u + ((chunk ^ ((uint32_t)(r + 3) & 7u)) << 4));
                         }
+                        if (l1 == l0) { v0 += v1; l1 = -1; }
+                        if (l2 == l0) { v0 += v2; l2 = -1; }
+                        if (l3 == l0) { v0 += v3; l3 = -1; }
+                        if (l2 == l1) { v1 += v2; l2 = -1; }
+                        if (l3 == l1) { v1 += v3; l3 = -1; }
+                        if (l3 == l2) { v2 += v3; l3 = -1; }
+                        // (merging two rows that are both skipped, label -1, is harmless)
+                        float *c0 = tab + (l0 < 0 ? 0 : l0) * acc_ld;
+                        float *c1 = tab + (l1 < 0 ? 0 : l1) * acc_ld;
+                        float *c2 = tab + (l2 < 0 ? 0 : l2) * acc_ld;
+                        float *c3 = tab + (l3 < 0 ? 0 : l3) * acc_ld;
+                        const float t0 = *c0, t1 = *c1, t2 = *c2, t3 = *c3;
+                        if (l0 >= 0) *c0 = t0 + v0;
+                        if (l1 >= 0) *c1 = t1 + v1;
+                        if (l2 >= 0) *c2 = t2 + v2;
+                        if (l3 >= 0) *c3 = t3 + v3;
                     }
                 }
                 bar_sync(1u + (uint32_t)g, 128);  // acc_lab is rewritten by the next tile
@@ -704,14 +981,29 @@ bmu_tc_kernel(const __grid_constant__ CUtensorMap tmX, const TcParams p)
             // all reads of this X stage by this warp are done
             __syncwarp();
             if (lane == 0) mbar_arrive(bar_empty + 8u * s);
-            // next tile of this group: NG stages further
-            s += NG;
-            if (s >= nstage) {
-                s -= nstage;
+            s += (uint32_t)NG;  // next tile of this group: NG stages further
+            if (s >= (uint32_t)nstage) {
+                s -= (uint32_t)nstage;
                 ph ^= 1u;
             }
         }
+    }
+    // ================================================================ end of step st
+    base_seq += cnt;
+    if constexpr (ACC) {
+        if (p.apply) {
+            __syncthreads();
+            if (blockIdx.x == 0 && threadIdx.x == 0) {
+                const uint64_t now = global_timer_ns();
+                p.ctl->phase_ns[0] += now - step_t0;
+            }
+            step_update<NG>(p, st, smem, gb_target);
+            if (blockIdx.x == 0 && threadIdx.x == 0) step_t0 = global_timer_ns();
+        }
+    }
+    }  // for st
 
+    if (warp < NEPI) {
         if (p.stats) {
             unsigned long long a = st_flag, b = st_pairs, c = st_fp64, d = st_fix;
             for (int o = 16; o > 0; o >>= 1) {
@@ -736,7 +1028,7 @@ bmu_tc_kernel(const __grid_constant__ CUtensorMap tmX, const TcParams p)
         tc_fence_after();
         tmem_dealloc(tmem_base, (uint32_t)pl.tmem_cols);
     }
-    if constexpr (ACC) {
+    if (ACC && !p.apply) {
         // ---- fused sums, part 2: groups are combined in group order into this CTA's partial,
         // then (grid barrier; every CTA is resident: grid <= SM count, one CTA per SM) each CTA
         // folds its slice of the table over all partials in CTA order, in fp64.

@@ -178,8 +178,9 @@ int bmu_tiles(const float *X, int64_t n, int C, int64_t ldX, const float *W, int
         // rows the tensor-core kernel could not settle (NaN/Inf rows, degenerate codebooks): exact
         // kernel; returns immediately when the counter is zero.  In fused mode it also adds those
         // rows to SN.
-        PX_CUDA(launch_bmu_exact(X, n, C, ldX, W, K, labels, tile_first, tile_stride, ntiles,
-                                 compact, &ws.aux->fixup_count, fused ? SN : nullptr, stream));
+        if (!fused)  // the fused (train-mode) kernel resolves those rows itself
+            PX_CUDA(launch_bmu_exact(X, n, C, ldX, W, K, labels, tile_first, tile_stride, ntiles,
+                                     compact, &ws.aux->fixup_count, nullptr, stream));
         if (stats) {
             set_u64_kernel<<<1, 1, 0, stream>>>(stats + PIXIE_STAT_KERNEL, 1ull);
             count_launch();
@@ -376,6 +377,56 @@ int pixie_som_train_f32(const float *X, int64_t n, int32_t C, int64_t ldX, doubl
     if ((env && env[0] == '1') || cap != cudaStreamCaptureStatusNone || dev < 0 || dev >= 64)
         return enqueue_train_steps(X, n, C, ldX, W64, W32, SN, xdim, ydim, rlen, batches_per_pass,
                                    alpha0, alpha1, radius0, radius1, workspace, ws_bytes, flags, st);
+
+    // ---- whole-pass kernel: every step of the run inside ONE persistent launch (BMU + fused sums,
+    // grid barrier, fold, batch update, codebook image rewrite) when the accumulators fit
+    {
+        const char *env2 = getenv("PIXIE_DISABLE_PERSISTENT");
+        TcPlan plan = make_tc_plan(C, K, true);
+        const bool aligned = ((reinterpret_cast<uintptr_t>(X) & 15u) == 0) && (ldX % 4 == 0) &&
+                             n < ((int64_t)1 << 31) - kTile && n > 0;
+        Workspace ws = carve(workspace, 0, C, K);
+        if (!workspace || ws_bytes < ws.total) return PIXIE_ERR_WORKSPACE;
+        CUtensorMap tm;
+        if (!(env2 && env2[0] == '1') && plan.ok && aligned && !(flags & PIXIE_FLAG_FORCE_EXACT) &&
+            make_x_tensor_map(&tm, X, n, C, ldX)) {
+            const int64_t T = (int64_t)rlen * batches_per_pass;
+            PX_CUDA(cudaMemsetAsync(ws.aux, 0, sizeof(CodebookAux), st));
+            PX_CUDA(cudaMemsetAsync(SN, 0, sizeof(double) * (size_t)K * (C + 1), st));
+            int rc = pixie_som_apply_f64(W64, W32, SN, xdim, ydim, C, 1.0, 0.0, st);  // W32 = fp32(W64)
+            if (rc != PIXIE_OK) return rc;
+            PX_CUDA(launch_codebook_prep(W32, K, C, plan, ws.wimg, ws.aux, st));
+            TcParams p{};
+            p.n = n;
+            p.tiles_total = (n + kTile - 1) / kTile;
+            p.ntiles = (p.tiles_total + batches_per_pass - 1) / batches_per_pass;  // sizes the grid
+            p.wimg = ws.wimg;
+            p.wimg_rw = ws.wimg;
+            p.labels = nullptr;
+            p.compact_labels = 0;
+            p.stats = nullptr;
+            p.ctl = ws.aux;
+            p.partials = ws.partials;
+            p.SN = SN;
+            p.nsteps = (int)T;
+            p.apply = 1;
+            p.B = batches_per_pass;
+            p.t0 = 0;
+            p.T = (int)T;
+            p.xdim = xdim;
+            p.ydim = ydim;
+            p.tile_offset = 0;
+            p.a0 = alpha0;
+            p.a1 = alpha1;
+            p.r0 = radius0;
+            p.r1 = radius1;
+            p.W64 = W64;
+            p.W32 = W32;
+            p.plan = plan;
+            PX_CUDA(launch_bmu_tc(tm, p, sum_parts(), st));
+            return PIXIE_OK;
+        }
+    }
 
     TrainKey key;
     memset(&key, 0, sizeof(key));

@@ -14,6 +14,7 @@ constexpr int kTile = PIXIE_TILE;  // rows per tile == UMMA M == TMEM lanes
 constexpr int kLabelFixup = -1;    // sentinel: row must be resolved by the exact fix-up kernel
 constexpr int kMaxCand = 15;       // candidate nodes kept per row before giving up to the fix-up
 constexpr int kWarpPairCap = 256;  // (row, node) pairs re-evaluated per tile by one epilogue warp
+constexpr int kWarpPairCapAcc = 256;  // ... in train mode, where shared memory also holds the sums
 constexpr int kMaxStages = 8;
 
 // Device-side result of the codebook preparation kernel, read by the BMU kernel.
@@ -23,7 +24,14 @@ struct CodebookAux {
     int fixup_count;  // rows the tensor-core kernel handed to the exact fix-up kernel
     int w_has_negative;  // any codebook entry with the sign bit set (disables the one-sided bound)
     unsigned int sums_sync[2];  // grid barrier of the cluster-sums kernel (self-resetting)
-    int pad[2];
+    // whole-pass kernel: codebook norms/flags of step t live in slot t & 1 (written by step t-1)
+    int pp_wmax_bits[2];
+    int pp_w_has_negative[2];
+    unsigned int grid_sync;  // its grid-barrier counter (zeroed per launch, only grows)
+    int pad[3];
+    // whole-pass kernel, CTA 0: nanoseconds spent in [tiles, barrier 1, fold, barrier 2, update,
+    // barrier 3], summed over steps (diagnostics; scripts/prof_train_pass.py reads them)
+    unsigned long long phase_ns[6];
 };
 
 // Host-side plan of the tensor-core BMU kernel for one (C, K).
@@ -48,6 +56,7 @@ struct TcPlan {
     uint32_t off_ones, off_x, off_bar, off_pairs;
     uint32_t off_acc, off_lab;  // fused accumulation (train mode): NG x K x (C+1) fp32, NG x 128 int
     int acc;                    // 1 = this plan has room for the fused accumulation
+    int pair_cap;               // pair-list capacity per epilogue warp
     uint32_t smem_bytes;  // dynamic shared memory to request (includes 1 KiB alignment slack)
 };
 
@@ -68,6 +77,21 @@ struct TcParams {
     // into SN [K][C+1] fp64 behind a grid barrier on ctl->sums_sync
     float *partials;
     double *SN;
+    // whole-pass mode (nsteps > 1 or apply != 0): the kernel runs `nsteps` mini-batch steps itself,
+    // step t visiting the tiles whose GLOBAL index is congruent to (t0 + t) % B, and after each
+    // step folds the sums, applies the batch update to W64/W32 and rewrites the codebook image.
+    int nsteps;            // 0/1 = single step described by tile_first/tile_stride/ntiles
+    int apply;             // 1 = fold + apply + re-prep inside the kernel
+    int B;                 // mini-batches per pass
+    int t0;                // index of the first step (for the schedule)
+    int T;                 // total steps of the run (schedule denominator)
+    int xdim, ydim;
+    int64_t tile_offset;   // global tile index of this shard's tile 0
+    int64_t tiles_total;   // ceil(n / 128)
+    double a0, a1, r0, r1; // learning-rate and radius ranges
+    double *W64;           // [K x C] master codebook
+    float *W32;            // [K x C] fp32 copy
+    float *wimg_rw;        // the codebook image again, writable (rows < K are rewritten per step)
     TcPlan plan;
 };
 
