@@ -22,7 +22,8 @@ STAT_ROWS_FLAGGED, STAT_PAIRS, STAT_ROWS_FP64, STAT_ROWS_FIXUP, STAT_KERNEL = 0,
 SYMBOLS = [
     "pixie_version", "pixie_error_string", "pixie_kernel_launches", "pixie_device_count", "pixie_workspace_bytes",
     "pixie_bmu_f32", "pixie_bmu_dist_f64", "pixie_cluster_sums_f32", "pixie_som_accum_f32", "pixie_som_apply_f64",
-    "pixie_som_train_f32", "pixie_map_data_to_nodes_host_f32", "pixie_map_data_to_nodes_host_f64",
+    "pixie_som_train_f32", "pixie_peer_buffer_bytes", "pixie_som_train_peers_f32",
+    "pixie_map_data_to_nodes_host_f32", "pixie_map_data_to_nodes_host_f64",
 ]
 
 _lib = None
@@ -82,6 +83,11 @@ def lib():
         L.pixie_som_apply_f64.argtypes = [vp, vp, vp, i32, i32, i32, dbl, dbl, vp]
         L.pixie_som_train_f32.argtypes = [vp, i64, i32, i64, vp, vp, vp, i32, i32, i32, i32, dbl,
                                           dbl, dbl, dbl, vp, sz, u32, vp]
+        L.pixie_peer_buffer_bytes.restype = sz
+        L.pixie_peer_buffer_bytes.argtypes = [i32, i32]
+        L.pixie_som_train_peers_f32.argtypes = [vp, i64, i32, i64, vp, vp, vp, i32, i32, i32, i32, dbl,
+                                                dbl, dbl, dbl, i64, i32, i32, vp, u32, vp, sz, u32, vp]
+        L.pixie_som_train_peers_f32.restype = c.c_int
         L.pixie_map_data_to_nodes_host_f32.argtypes = [vp, i32, vp, i64, i32, vp, vp, i32, i64]
         L.pixie_map_data_to_nodes_host_f64.argtypes = [vp, i32, vp, i64, i32, vp, vp, i32, i64]
         for name in ("pixie_bmu_f32", "pixie_bmu_dist_f64", "pixie_cluster_sums_f32", "pixie_som_accum_f32",

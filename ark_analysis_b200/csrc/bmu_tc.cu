@@ -353,6 +353,7 @@ __device__ __noinline__ void step_update(const TcParams &p, int st, uint8_t *sme
     lap(1);
 
     // 2. every CTA folds its slice of the table over all partials, CTA order, fp64
+    double *fold_dst = p.world > 1 ? p.peer_buf[p.rank] + (size_t)(st & 1) * len : p.SN;
     {
         const int nparts = gridDim.x;
         const int per = (len + nparts - 1) / nparts;
@@ -374,7 +375,53 @@ __device__ __noinline__ void step_update(const TcParams &p, int st, uint8_t *sme
             a += __shfl_xor_sync(0xffffffffu, a, 1);
             a += __shfl_xor_sync(0xffffffffu, a, 2);
             a += __shfl_xor_sync(0xffffffffu, a, 4);
-            if (e < e1 && q == 0) p.SN[e] = a;
+            if (e < e1 && q == 0) fold_dst[e] = a;
+        }
+    }
+    if (p.world > 1) {
+        // ---- cross-GPU sum over NVLink peer memory, fused into the step: every rank has folded
+        // its shard's table into its exchange buffer; after a flag handshake each CTA sums ITS
+        // slice over the ranks in rank order (so every rank computes bit-identical totals).
+        gb_target += gridDim.x;
+        grid_barrier(gsync, gb_target);  // this rank's buffer is complete
+        if (blockIdx.x == 0 && tid == 0) {
+            __threadfence_system();
+            const uint32_t val = p.flag_base + (uint32_t)st + 1u;
+            const size_t flag_off = (size_t)2 * len * sizeof(double);
+            for (int r = 0; r < p.world; ++r) {
+                if (r == p.rank) continue;
+                uint32_t *dst = reinterpret_cast<uint32_t *>(
+                                    reinterpret_cast<char *>(p.peer_buf[r]) + flag_off) + p.rank;
+                asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(dst), "r"(val) : "memory");
+            }
+            const uint32_t *mine_flags = reinterpret_cast<const uint32_t *>(
+                reinterpret_cast<const char *>(p.peer_buf[p.rank]) + flag_off);
+            for (int r = 0; r < p.world; ++r) {
+                if (r == p.rank) continue;
+                uint32_t seen, spins = 0;
+                do {
+                    asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(seen) : "l"(mine_flags + r) : "memory");
+                    if (seen - val < 0x80000000u) break;  // seen >= val (wrap-safe)
+                    __nanosleep(64);
+                    if (++spins > (1u << 26)) __trap();  // a peer died: fail instead of hanging
+                } while (true);
+            }
+        }
+        gb_target += gridDim.x;
+        grid_barrier(gsync, gb_target);  // all ranks' buffers are complete and visible
+        const int nparts = gridDim.x;
+        const int per = (len + nparts - 1) / nparts;
+        const int e0 = blockIdx.x * per;
+        const int e1 = min(len, e0 + per);
+        for (int e = e0 + tid; e < e1; e += nthr) {
+            double a = 0.0;
+            for (int r = 0; r < p.world; ++r) {
+                double v;
+                const double *src = p.peer_buf[r] + (size_t)(st & 1) * len + e;
+                asm volatile("ld.volatile.global.f64 %0, [%1];" : "=d"(v) : "l"(src) : "memory");
+                a += v;
+            }
+            p.SN[e] = a;
         }
     }
     if (blockIdx.x == 0 && tid == 0) {
@@ -645,13 +692,19 @@ bmu_tc_kernel(const __grid_constant__ CUtensorMap tmX, const TcParams p)
         const uint32_t it0 = ((uint32_t)g + (uint32_t)NG - base_seq % (uint32_t)NG) % (uint32_t)NG;
         uint32_t s = (base_seq + it0) % (uint32_t)nstage;          // one division per step, then
         uint32_t ph = ((base_seq + it0) / (uint32_t)nstage) & 1u;  // incremental (+NG per tile)
-        for (uint32_t it = it0; it < cnt; it += (uint32_t)NG) {
+        // row / label cursors advance by a constant per tile of this group (no 64-bit multiplies
+        // in the tile loop)
+        const int64_t j0 = (int64_t)blockIdx.x + (int64_t)it0 * gridDim.x;
+        const int64_t jstep = (int64_t)NG * gridDim.x;
+        int64_t grow = (stp.first + j0 * stp.stride) * kTile + row;  // global row
+        const int64_t grow_step = jstep * stp.stride * kTile;
+        int32_t *lab_ptr =
+            p.labels ? p.labels + (p.compact_labels ? j0 * kTile + row : grow) : nullptr;
+        const int64_t lab_step = p.labels ? (p.compact_labels ? jstep * kTile : grow_step) : 0;
+        for (uint32_t it = it0; it < cnt;
+             it += (uint32_t)NG, grow += grow_step, lab_ptr += lab_step) {
             const uint32_t seq = base_seq + it;
             const uint32_t use = seq / (uint32_t)NG;  // NG is a power of two: a shift
-            const int64_t j = (int64_t)blockIdx.x + (int64_t)it * gridDim.x;
-            const int64_t grow = (stp.first + j * stp.stride) * kTile + row;  // global row
-            int32_t *lab_ptr =
-                p.labels ? p.labels + (p.compact_labels ? j * kTile + row : grow) : nullptr;
             const uint8_t *xs = xs0 + (uint32_t)s * pl.stage_bytes;
 
             mbar_wait(bar_full + 8u * s, ph);  // X tile landed

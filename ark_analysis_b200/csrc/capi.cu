@@ -301,6 +301,68 @@ int pixie_som_apply_f64(double *W64, float *W32, const double *SN, int32_t xdim,
     return PIXIE_OK;
 }
 
+// The whole training run as one persistent launch.  PIXIE_ERR_UNSUPPORTED when the shape has no
+// plan with room for the fused accumulators (callers fall back to the step-by-step path).
+static int launch_whole_pass(const float *X, int64_t n, int32_t C, int64_t ldX, double *W64,
+                             float *W32, double *SN, int32_t xdim, int32_t ydim, int32_t rlen,
+                             int32_t batches_per_pass, double alpha0, double alpha1, double radius0,
+                             double radius1, int64_t tile_offset, int32_t world, int32_t rank,
+                             const uint64_t *peer_bufs, uint32_t flag_base, void *workspace,
+                             size_t ws_bytes, uint32_t flags, cudaStream_t st)
+{
+    const int K = xdim * ydim;
+    TcPlan plan = make_tc_plan(C, K, true);
+    const bool aligned = ((reinterpret_cast<uintptr_t>(X) & 15u) == 0) && (ldX % 4 == 0) &&
+                         n < ((int64_t)1 << 31) - kTile && n > 0;
+    Workspace ws = carve(workspace, 0, C, K);
+    if (!workspace || ws_bytes < ws.total) return PIXIE_ERR_WORKSPACE;
+    CUtensorMap tm;
+    if (!plan.ok || !aligned || (flags & PIXIE_FLAG_FORCE_EXACT) || world < 1 || world > 8 ||
+        !make_x_tensor_map(&tm, X, n, C, ldX))
+        return PIXIE_ERR_UNSUPPORTED;
+    const int64_t T = (int64_t)rlen * batches_per_pass;
+    PX_CUDA(cudaMemsetAsync(ws.aux, 0, sizeof(CodebookAux), st));
+    PX_CUDA(cudaMemsetAsync(SN, 0, sizeof(double) * (size_t)K * (C + 1), st));
+    int rc = pixie_som_apply_f64(W64, W32, SN, xdim, ydim, C, 1.0, 0.0, st);  // W32 = fp32(W64)
+    if (rc != PIXIE_OK) return rc;
+    PX_CUDA(launch_codebook_prep(W32, K, C, plan, ws.wimg, ws.aux, st));
+    TcParams p{};
+    p.n = n;
+    p.tiles_total = (n + kTile - 1) / kTile;
+    p.ntiles = (p.tiles_total + batches_per_pass - 1) / batches_per_pass;  // sizes the grid
+    if (world > 1) p.ntiles = sum_parts();  // every rank runs the full grid (equal barrier counts)
+    p.wimg = ws.wimg;
+    p.wimg_rw = ws.wimg;
+    p.labels = nullptr;
+    p.compact_labels = 0;
+    p.stats = nullptr;
+    p.ctl = ws.aux;
+    p.partials = ws.partials;
+    p.SN = SN;
+    p.nsteps = (int)T;
+    p.apply = 1;
+    p.B = batches_per_pass;
+    p.t0 = 0;
+    p.T = (int)T;
+    p.xdim = xdim;
+    p.ydim = ydim;
+    p.tile_offset = tile_offset;
+    p.a0 = alpha0;
+    p.a1 = alpha1;
+    p.r0 = radius0;
+    p.r1 = radius1;
+    p.W64 = W64;
+    p.W32 = W32;
+    p.world = world;
+    p.rank = rank;
+    p.flag_base = flag_base;
+    for (int r = 0; r < 8; ++r)
+        p.peer_buf[r] = (world > 1 && r < world) ? reinterpret_cast<double *>(peer_bufs[r]) : nullptr;
+    p.plan = plan;
+    PX_CUDA(launch_bmu_tc(tm, p, sum_parts(), st));
+    return PIXIE_OK;
+}
+
 // Enqueues the T = rlen * B accumulate + apply steps on `st` (no host synchronisation).
 static int enqueue_train_steps(const float *X, int64_t n, int32_t C, int64_t ldX, double *W64,
                                float *W32, double *SN, int32_t xdim, int32_t ydim, int32_t rlen,
@@ -382,49 +444,11 @@ int pixie_som_train_f32(const float *X, int64_t n, int32_t C, int64_t ldX, doubl
     // grid barrier, fold, batch update, codebook image rewrite) when the accumulators fit
     {
         const char *env2 = getenv("PIXIE_DISABLE_PERSISTENT");
-        TcPlan plan = make_tc_plan(C, K, true);
-        const bool aligned = ((reinterpret_cast<uintptr_t>(X) & 15u) == 0) && (ldX % 4 == 0) &&
-                             n < ((int64_t)1 << 31) - kTile && n > 0;
-        Workspace ws = carve(workspace, 0, C, K);
-        if (!workspace || ws_bytes < ws.total) return PIXIE_ERR_WORKSPACE;
-        CUtensorMap tm;
-        if (!(env2 && env2[0] == '1') && plan.ok && aligned && !(flags & PIXIE_FLAG_FORCE_EXACT) &&
-            make_x_tensor_map(&tm, X, n, C, ldX)) {
-            const int64_t T = (int64_t)rlen * batches_per_pass;
-            PX_CUDA(cudaMemsetAsync(ws.aux, 0, sizeof(CodebookAux), st));
-            PX_CUDA(cudaMemsetAsync(SN, 0, sizeof(double) * (size_t)K * (C + 1), st));
-            int rc = pixie_som_apply_f64(W64, W32, SN, xdim, ydim, C, 1.0, 0.0, st);  // W32 = fp32(W64)
-            if (rc != PIXIE_OK) return rc;
-            PX_CUDA(launch_codebook_prep(W32, K, C, plan, ws.wimg, ws.aux, st));
-            TcParams p{};
-            p.n = n;
-            p.tiles_total = (n + kTile - 1) / kTile;
-            p.ntiles = (p.tiles_total + batches_per_pass - 1) / batches_per_pass;  // sizes the grid
-            p.wimg = ws.wimg;
-            p.wimg_rw = ws.wimg;
-            p.labels = nullptr;
-            p.compact_labels = 0;
-            p.stats = nullptr;
-            p.ctl = ws.aux;
-            p.partials = ws.partials;
-            p.SN = SN;
-            p.nsteps = (int)T;
-            p.apply = 1;
-            p.B = batches_per_pass;
-            p.t0 = 0;
-            p.T = (int)T;
-            p.xdim = xdim;
-            p.ydim = ydim;
-            p.tile_offset = 0;
-            p.a0 = alpha0;
-            p.a1 = alpha1;
-            p.r0 = radius0;
-            p.r1 = radius1;
-            p.W64 = W64;
-            p.W32 = W32;
-            p.plan = plan;
-            PX_CUDA(launch_bmu_tc(tm, p, sum_parts(), st));
-            return PIXIE_OK;
+        if (!(env2 && env2[0] == '1')) {
+            int rc = launch_whole_pass(X, n, C, ldX, W64, W32, SN, xdim, ydim, rlen,
+                                       batches_per_pass, alpha0, alpha1, radius0, radius1, 0, 1, 0,
+                                       nullptr, 0u, workspace, ws_bytes, flags, st);
+            if (rc != PIXIE_ERR_UNSUPPORTED) return rc;
         }
     }
 
@@ -481,6 +505,32 @@ int pixie_som_train_f32(const float *X, int64_t n, int32_t C, int64_t ldX, doubl
     PX_CUDA(cudaGraphLaunch(exec, st));
     count_launch((int)per_replay);
     return PIXIE_OK;
+}
+
+size_t pixie_peer_buffer_bytes(int32_t C, int32_t K)
+{
+    if (C < 1 || K < 1) return 0;
+    return (size_t)2 * K * (C + 1) * sizeof(double) + 8 * sizeof(uint32_t) + 224;
+}
+
+int pixie_som_train_peers_f32(const float *X, int64_t n, int32_t C, int64_t ldX, double *W64,
+                              float *W32, double *SN, int32_t xdim, int32_t ydim, int32_t rlen,
+                              int32_t batches_per_pass, double alpha0, double alpha1,
+                              double radius0, double radius1, int64_t tile_offset, int32_t world,
+                              int32_t rank, const uint64_t *peer_bufs, uint32_t flag_base,
+                              void *workspace, size_t ws_bytes, uint32_t flags, void *stream)
+{
+    if (xdim < 1 || ydim < 1 || rlen < 1 || batches_per_pass < 1 || !W64 || !W32 || !SN ||
+        world < 2 || world > 8 || rank < 0 || rank >= world || !peer_bufs || tile_offset < 0)
+        return PIXIE_ERR_INVALID_ARG;
+    const int K = xdim * ydim;
+    if (bad_shape(n, C, ldX, K) || (n > 0 && !X)) return PIXIE_ERR_INVALID_ARG;
+    for (int r = 0; r < world; ++r)
+        if (!peer_bufs[r]) return PIXIE_ERR_INVALID_ARG;
+    return launch_whole_pass(X, n, C, ldX, W64, W32, SN, xdim, ydim, rlen, batches_per_pass, alpha0,
+                             alpha1, radius0, radius1, tile_offset, world, rank, peer_bufs,
+                             flag_base, workspace, ws_bytes, flags,
+                             reinterpret_cast<cudaStream_t>(stream));
 }
 
 }  // extern "C"

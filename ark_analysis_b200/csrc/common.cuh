@@ -92,6 +92,11 @@ struct TcParams {
     double *W64;           // [K x C] master codebook
     float *W32;            // [K x C] fp32 copy
     float *wimg_rw;        // the codebook image again, writable (rows < K are rewritten per step)
+    // multi-GPU whole-pass mode: every rank's exchange buffer ([2][K x (C+1)] fp64 ping-pong + one
+    // uint32 flag per source rank), mapped into this process (NVLink peer memory)
+    int world, rank;
+    uint32_t flag_base;    // flags only grow: step st of this launch signals flag_base + st + 1
+    double *peer_buf[8];
     TcPlan plan;
 };
 

@@ -257,6 +257,24 @@ def train_som(X, W0, xdim, ydim, rlen=1, alpha_range=(0.05, 0.01), radius_range=
         _native.check(rc, "pixie_som_train_f32")
         return W64
     import torch.distributed as dist
+    # Preferred: the whole run in ONE persistent kernel per rank, the per-step statistics summed
+    # across GPUs inside the kernel over NVLink peer memory (symmetric memory mapped by torch).
+    peers = _peer_exchange(K, C, dev, group)
+    if peers is not None:
+        ptrs, base = peers.claim(int(rlen) * B)
+        with torch.cuda.device(dev):
+            ws = _workspace(0, C, K, dev)
+            arr = (ctypes.c_uint64 * len(ptrs))(*ptrs)
+            rc = _native.lib().pixie_som_train_peers_f32(
+                _ptr(X), n, C, ld, _ptr(W64), _ptr(W32), _ptr(SN), xdim, ydim, int(rlen), B,
+                float(alpha_range[0]), float(alpha_range[1]), float(radius_range[0]),
+                float(radius_range[1]), int(tile_offset), dist.get_world_size(group),
+                dist.get_rank(group), arr, base, _ptr(ws), ws.numel(), flags, _stream(dev))
+        if rc == 0:
+            return W64
+        if rc != -4:  # anything but "shape not supported" is an error
+            _native.check(rc, "pixie_som_train_peers_f32")
+    # Fallback: one accumulate launch, one NCCL all-reduce and one apply launch per step.
     som_apply(W64, W32, SN, xdim, ydim, 1.0, 0.0)  # W32 = fp32(W64)
     run_training_steps(
         rlen, B, int(tile_offset), alpha_range, radius_range,
@@ -264,6 +282,53 @@ def train_som(X, W0, xdim, ydim, rlen=1, alpha_range=(0.05, 0.01), radius_range=
         allreduce=lambda stats: dist.all_reduce(stats, op=dist.ReduceOp.SUM, group=group),
         apply=lambda stats, sigma, alpha: som_apply(W64, W32, stats, xdim, ydim, sigma, alpha))
     return W64
+
+
+class _PeerExchange:
+    """Per (group, K, C) symmetric exchange buffers for pixie_som_train_peers_f32."""
+
+    def __init__(self, buf, ptrs):
+        self.buf = buf          # keeps the symmetric allocation alive
+        self.ptrs = ptrs        # device pointers of every rank's buffer, mapped in this process
+        self.flag_base = 0
+
+    def claim(self, nsteps):
+        base = self.flag_base
+        self.flag_base = (self.flag_base + nsteps + 1) & 0x7FFFFFFF
+        return self.ptrs, base
+
+
+_peer_cache = {}
+
+
+def _peer_exchange(K, C, dev, group):
+    """Symmetric-memory exchange buffers, or None when torch cannot provide peer mappings (the
+    NCCL step loop is used then).  Collective: every rank of `group` must call it."""
+    import os
+    if os.environ.get("PIXIE_DISABLE_PEER", "0") == "1":
+        return None
+    key = (id(group), K, C, dev.index)
+    if key in _peer_cache:
+        return _peer_cache[key]
+    peers = None
+    try:
+        import torch.distributed as dist
+        import torch.distributed._symmetric_memory as symm_mem
+        nbytes = _native.lib().pixie_peer_buffer_bytes(int(C), int(K))
+        buf = symm_mem.empty((nbytes + 7) // 8, dtype=torch.float64, device=dev)
+        buf.zero_()
+        hdl = symm_mem.rendezvous(buf, group)
+        ptrs = [int(p) for p in hdl.buffer_ptrs]
+        torch.cuda.synchronize(dev)
+        dist.barrier(group=group)  # every rank's buffer is zeroed before anyone signals into it
+        if len(ptrs) == dist.get_world_size(group) and all(ptrs):
+            peers = _PeerExchange(buf, ptrs)
+    except Exception as exc:  # noqa: BLE001 -- any failure here just selects the NCCL loop
+        import warnings
+        warnings.warn(f"peer-memory exchange unavailable ({exc!r}); using the NCCL step loop")
+        peers = None
+    _peer_cache[key] = peers
+    return peers
 
 
 # ------------------------------------------------------------------------------------------------

@@ -120,6 +120,25 @@ int pixie_som_train_f32(const float *X, int64_t n, int32_t C, int64_t ldX, doubl
                         void *stream);
 
 /*
+ * Multi-GPU form of pixie_som_train_f32: one call per rank (one process per GPU), all ranks at the
+ * same time.  X is this rank's row shard, whose first row is GLOBAL tile `tile_offset`.  The
+ * per-step statistics are summed across ranks INSIDE the training kernel over NVLink peer memory
+ * (no NCCL call, no host synchronisation): `peer_bufs` is a HOST array of `world` device pointers,
+ * entry r being rank r's exchange buffer mapped into this process (CUDA IPC / symmetric memory),
+ * each at least pixie_peer_buffer_bytes(C, K) bytes, zero-initialised once.  `flag_base` must grow
+ * by at least rlen * batches_per_pass between successive calls on the same buffers.  Every rank
+ * ends with the bit-identical codebook.  Returns PIXIE_ERR_UNSUPPORTED when the shape does not fit
+ * the persistent kernel (the caller then runs pixie_som_accum_f32 + all-reduce + apply per step).
+ */
+size_t pixie_peer_buffer_bytes(int32_t C, int32_t K);
+int pixie_som_train_peers_f32(const float *X, int64_t n, int32_t C, int64_t ldX, double *W64,
+                              float *W32, double *SN, int32_t xdim, int32_t ydim, int32_t rlen,
+                              int32_t batches_per_pass, double alpha0, double alpha1,
+                              double radius0, double radius1, int64_t tile_offset, int32_t world,
+                              int32_t rank, const uint64_t *peer_bufs, uint32_t flag_base,
+                              void *workspace, size_t ws_bytes, uint32_t flags, void *stream);
+
+/*
  * Host-buffer entry point with pyFlowSOM.map_data_to_nodes' shape (what a ctypes/cgo/JNI binding
  * of the reference would call): nodes [K x C] and data [n x C] in HOST memory (fp32, row-major,
  * contiguous), labels int32[n] and optional dists double[n] in host memory.  Streams the rows
