@@ -556,7 +556,8 @@ bmu_tc_kernel(const __grid_constant__ CUtensorMap tmX, const TcParams p)
         reinterpret_cast<volatile uint32_t *>(smem + pl.off_bar + 16u * kMaxStages + 72u);
 
     const int nstage = pl.nstage;
-    const int nsteps = p.nsteps > 1 ? p.nsteps : 1;
+    // plain assignment (ACC == false) is always a single step: let the compiler drop the loop
+    const int nsteps = ACC ? (p.nsteps > 1 ? p.nsteps : 1) : 1;
 
     // ---------------------------------------------------------------- one-time setup
     if (warp == NEPI && lane == 0) {
@@ -596,7 +597,7 @@ bmu_tc_kernel(const __grid_constant__ CUtensorMap tmX, const TcParams p)
     uint32_t st_flag = 0, st_pairs = 0, st_fp64 = 0, st_fix = 0;  // per-thread statistics
     uint64_t step_t0 = (ACC && blockIdx.x == 0 && threadIdx.x == 0) ? global_timer_ns() : 0;  // grid-barrier instances passed so far x gridDim.x
     for (int st = 0; st < nsteps; ++st) {
-    const StepTiles stp = step_tiles(p, st);
+    const StepTiles stp = ACC ? step_tiles(p, st) : StepTiles{p.tile_first, p.tile_stride, p.ntiles};
     const int64_t ntiles = stp.count;
     const uint32_t cnt =
         (int64_t)blockIdx.x < ntiles ? (uint32_t)((ntiles - blockIdx.x + gridDim.x - 1) / gridDim.x) : 0u;
@@ -678,9 +679,10 @@ bmu_tc_kernel(const __grid_constant__ CUtensorMap tmX, const TcParams p)
         mbar_wait(bar_w, (uint32_t)st & 1u);  // codebook image visible to this thread
         // norms of the codebook this step runs against: written by the prep kernel for the first
         // step, by the previous step's in-kernel update (ping-pong slot) afterwards
-        const float wmax = __int_as_float(st == 0 ? p.ctl->wmax_bits : p.ctl->pp_wmax_bits[st & 1]);
+        const float wmax = __int_as_float((!ACC || st == 0) ? p.ctl->wmax_bits : p.ctl->pp_wmax_bits[st & 1]);
         const float wmax2 = wmax * wmax;
-        const bool w_nonneg = (st == 0 ? p.ctl->w_has_negative : p.ctl->pp_w_has_negative[st & 1]) == 0;
+        const bool w_nonneg =
+            ((!ACC || st == 0) ? p.ctl->w_has_negative : p.ctl->pp_w_has_negative[st & 1]) == 0;
         // fused accumulation (train mode)
         constexpr bool do_acc = ACC;
         const int acc_ld = pl.C + 1;
