@@ -39,6 +39,14 @@ def _worker(rank, world, port, X, W0, out):
                     tile_offset=lo // 128)
     labels = S.bmu(Xd, W.to(torch.float32))
     torch.cuda.synchronize()
+    # the fused peer-memory path (not the NCCL fallback) must have been taken
+    assert any(v is not None for v in S._peer_cache.values()), "peer-memory exchange not used"
+    # and the NCCL step loop gives the same codebook
+    os.environ["PIXIE_DISABLE_PEER"] = "1"
+    S._peer_cache.clear()
+    W2 = S.train_som(Xd, W0, XD, YD, rlen=2, batches_per_pass=B, group=dist.group.WORLD,
+                     tile_offset=lo // 128)
+    assert float((W2 - W).abs().max()) <= 1e-9 * float(W.abs().max())
     np.save(out % ("w", rank), W.cpu().numpy())
     np.save(out % ("l", rank), labels.cpu().numpy())
     dist.destroy_process_group()
