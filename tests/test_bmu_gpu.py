@@ -240,3 +240,31 @@ def test_full_size_properties_cfg2():
     # oracle spot check on a window the CPU finishes in seconds
     ref, _ = oracle.map_data_to_nodes_f32(W.cpu().numpy(), X[:300_000].cpu().numpy())
     np.testing.assert_array_equal(lab[:300_000].cpu().numpy(), ref)
+
+
+def _full_size_properties(n, C, K, windows):
+    g = torch.Generator(device="cuda").manual_seed(7)
+    X = torch.rand((n, C), device="cuda", generator=g)
+    W = X[torch.randperm(n, device="cuda", generator=g)[:K]].contiguous()
+    lab, SN = S.cluster_sums(X, W)
+    assert int(lab.min()) >= 1 and int(lab.max()) <= K
+    assert torch.equal(lab, S.bmu(X, W))  # deterministic, with and without the fused sums
+    cnt = SN[:, C].cpu().numpy()
+    assert cnt.sum() == n
+    np.testing.assert_array_equal(cnt, torch.bincount(lab.long(), minlength=K + 1)[1:].cpu().numpy())
+    assert float(S.bmu_dists(X, W, lab).min()) == 0.0  # codebook rows map to themselves
+    for lo in windows:
+        sl = slice(lo, lo + 200_000)
+        assert torch.equal(lab[sl], S.bmu(X[sl], W, flags=S.FLAG_FORCE_EXACT))
+    ref, _ = oracle.map_data_to_nodes_f32(W.cpu().numpy(), X[:100_000].cpu().numpy())
+    np.testing.assert_array_equal(lab[:100_000].cpu().numpy(), ref)
+
+
+def test_full_size_properties_cfg4_cells():
+    """BASELINE.json config 4: 5 M cells x 100 features, 10x10 SOM."""
+    _full_size_properties(5_000_000, 100, 100, (0, 2_500_000, 4_800_000))
+
+
+def test_full_size_properties_cfg3_shard_slice():
+    """BASELINE.json config 3 shape (40 channels, 20x20 SOM) on 8 of a GPU's 62 FOVs of 2048^2."""
+    _full_size_properties(8 * 2048 * 2048, 40, 400, (0, 16_000_000, 33_000_000))
