@@ -1155,9 +1155,20 @@ static cudaError_t launch_acc(const CUtensorMap &tmX, const TcParams &p, int gri
                                          cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          (int)p.plan.smem_bytes);
     if (e != cudaSuccess) return e;
-    bmu_tc_kernel<SL, SPC, NCH, NG, ACC><<<grid, NG * 128 + 64, p.plan.smem_bytes, stream>>>(tmX, p);
-    count_launch();
-    return cudaGetLastError();
+    if constexpr (ACC) {
+        // the fused-sums variants use grid-wide barriers: launch cooperatively so the runtime
+        // guarantees (or refuses) co-residency of all CTAs
+        void *args[] = {const_cast<CUtensorMap *>(&tmX), const_cast<TcParams *>(&p)};
+        e = cudaLaunchCooperativeKernel(
+            reinterpret_cast<const void *>(&bmu_tc_kernel<SL, SPC, NCH, NG, ACC>), dim3(grid),
+            dim3(NG * 128 + 64), args, p.plan.smem_bytes, stream);
+        count_launch();
+        return e;
+    } else {
+        bmu_tc_kernel<SL, SPC, NCH, NG, ACC><<<grid, NG * 128 + 64, p.plan.smem_bytes, stream>>>(tmX, p);
+        count_launch();
+        return cudaGetLastError();
+    }
 }
 
 template <int SL, int SPC, int NCH, int NG>

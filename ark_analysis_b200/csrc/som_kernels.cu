@@ -339,16 +339,22 @@ cudaError_t launch_cluster_sums(const float *X, int64_t n, int C, int64_t ldX,
         e = cudaFuncSetAttribute(cluster_sums_kernel<true>,
                                  cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_acc);
         if (e != cudaSuccess) return e;
-        cluster_sums_kernel<true><<<grid, kSumThreads, smem_acc, stream>>>(
-            X, n, C, ldX, labels, compact_labels, K, tile_first, tile_stride, ntiles, partials, SN,
-            ticket);
+        void *args[] = {&X, &n, &C, &ldX, &labels, &compact_labels, &K, &tile_first, &tile_stride,
+                        &ntiles, &partials, &SN, &ticket};
+        e = cudaLaunchCooperativeKernel(reinterpret_cast<const void *>(&cluster_sums_kernel<true>),
+                                        dim3(grid), dim3(kSumThreads), args, smem_acc, stream);
+        count_launch();
+        return e;
     } else {
         e = cudaFuncSetAttribute(cluster_sums_kernel<false>,
                                  cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_noacc);
         if (e != cudaSuccess) return e;
-        cluster_sums_kernel<false><<<grid, kSumThreads, smem_noacc, stream>>>(
-            X, n, C, ldX, labels, compact_labels, K, tile_first, tile_stride, ntiles, partials, SN,
-            ticket);
+        void *args[] = {&X, &n, &C, &ldX, &labels, &compact_labels, &K, &tile_first, &tile_stride,
+                        &ntiles, &partials, &SN, &ticket};
+        e = cudaLaunchCooperativeKernel(reinterpret_cast<const void *>(&cluster_sums_kernel<false>),
+                                        dim3(grid), dim3(kSumThreads), args, smem_noacc, stream);
+        count_launch();
+        return e;
     }
     count_launch();
     return cudaGetLastError();
