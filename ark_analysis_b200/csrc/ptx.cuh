@@ -13,17 +13,6 @@ __device__ __forceinline__ uint32_t smem_u32(const void *p)
     return static_cast<uint32_t>(__cvta_generic_to_shared(p));
 }
 
-__device__ __forceinline__ bool elect_one()
-{
-    uint32_t pred = 0;
-    asm volatile(
-        "{\n\t.reg .pred P;\n\t.reg .b32 R;\n\t"
-        "elect.sync R|P, 0xffffffff;\n\t"
-        "selp.b32 %0, 1, 0, P;\n\t}\n"
-        : "=r"(pred));
-    return pred != 0;
-}
-
 // ---------------------------------------------------------------- mbarrier
 __device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count)
 {
@@ -87,7 +76,6 @@ __device__ __forceinline__ void prefetch_tensormap(const void *tmap)
     asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(tmap)) : "memory");
 }
 constexpr uint64_t kEvictFirst = 0x12F0000000000000ull;
-constexpr uint64_t kEvictLast = 0x14F0000000000000ull;
 
 __device__ __forceinline__ void tma_load_2d(uint32_t dst_smem, const void *tmap, uint32_t bar,
                                             int32_t c0, int32_t c1, uint64_t cache_hint)
