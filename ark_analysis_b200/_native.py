@@ -41,7 +41,7 @@ def build(force=False, verbose=False):
     stale = force or not os.path.exists(LIB_PATH) or any(
         os.path.getmtime(s) > os.path.getmtime(LIB_PATH) for s in srcs)
     if stale:
-        cmd = ["make", "-C", CSRC] + (["-B"] if force else [])
+        cmd = ["make", "-j", str(min(8, os.cpu_count() or 1)), "-C", CSRC] + (["-B"] if force else [])
         out = subprocess.run(cmd, capture_output=True, text=True)
         if verbose or out.returncode != 0:
             print(out.stdout)

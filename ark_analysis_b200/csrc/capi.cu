@@ -101,6 +101,16 @@ int sum_parts()
     return sms < kSumParts ? sms : kSumParts;
 }
 
+// Candidate-window scale: 1 in production.  PIXIE_DELTA_SCALE < 1 shrinks the tensor-core
+// candidate window below its proven bound -- tests use it to measure how much margin the bound has.
+float delta_scale_from_env()
+{
+    const char *v = getenv("PIXIE_DELTA_SCALE");
+    if (!v || !v[0]) return 1.0f;
+    const float f = (float)atof(v);
+    return (f > 0.f && f <= 64.f) ? f : 1.0f;
+}
+
 // ---- workspace carve-up
 struct Workspace {
     float *wimg;
@@ -173,6 +183,7 @@ int bmu_tiles(const float *X, int64_t n, int C, int64_t ldX, const float *W, int
         p.ctl = ws.aux;
         p.partials = fused ? ws.partials : nullptr;
         p.SN = fused ? SN : nullptr;
+        p.delta_scale = delta_scale_from_env();
         p.plan = plan;
         PX_CUDA(launch_bmu_tc(tm, p, sum_parts(), stream));
         // rows the tensor-core kernel could not settle (NaN/Inf rows, degenerate codebooks): exact
@@ -356,6 +367,7 @@ static int launch_whole_pass(const float *X, int64_t n, int32_t C, int64_t ldX, 
     p.world = world;
     p.rank = rank;
     p.flag_base = flag_base;
+    p.delta_scale = delta_scale_from_env();
     for (int r = 0; r < 8; ++r)
         p.peer_buf[r] = (world > 1 && r < world) ? reinterpret_cast<double *>(peer_bufs[r]) : nullptr;
     p.plan = plan;

@@ -16,6 +16,7 @@ constexpr int kMaxCand = 15;       // candidate nodes kept per row before giving
 constexpr int kWarpPairCap = 256;  // (row, node) pairs re-evaluated per tile by one epilogue warp
 constexpr int kWarpPairCapAcc = 256;  // ... in train mode, where shared memory also holds the sums
 constexpr int kMaxStages = 8;
+constexpr int kBarBlock = 256;     // bytes of shared memory reserved for mbarriers
 
 // Device-side result of the codebook preparation kernel, read by the BMU kernel.
 struct CodebookAux {
@@ -60,7 +61,8 @@ struct TcPlan {
     uint32_t smem_bytes;  // dynamic shared memory to request (includes 1 KiB alignment slack)
 };
 
-// acc = true: also reserve per-group fp32 accumulators for the fused per-node sums (train mode)
+// acc = true: also reserve per-group fp32 accumulators for the fused per-node sums (train mode).
+// PIXIE_TC_STAGES (environment, experiments only) caps the pipeline depth.
 TcPlan make_tc_plan(int C, int K, bool acc = false);
 
 struct TcParams {
@@ -97,6 +99,7 @@ struct TcParams {
     int world, rank;
     uint32_t flag_base;    // flags only grow: step st of this launch signals flag_base + st + 1
     double *peer_buf[8];
+    float delta_scale;     // 1 in production; tests shrink the candidate window to probe its margin
     TcPlan plan;
 };
 
