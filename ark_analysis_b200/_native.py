@@ -21,7 +21,8 @@ STAT_ROWS_FLAGGED, STAT_PAIRS, STAT_ROWS_FP64, STAT_ROWS_FIXUP, STAT_KERNEL = 0,
 # every symbol include/pixie_b200.h declares (checked by tests/test_capi_symbols.py)
 SYMBOLS = [
     "pixie_version", "pixie_error_string", "pixie_kernel_launches", "pixie_device_count", "pixie_workspace_bytes",
-    "pixie_bmu_f32", "pixie_bmu_dist_f64", "pixie_cluster_sums_f32", "pixie_som_accum_f32", "pixie_som_apply_f64",
+    "pixie_bmu_f32", "pixie_bmu_dist_f64", "pixie_cluster_sums_f32", "pixie_columns_to_rows_f32", "pixie_som_online_f64", "pixie_libc_sample_indices",
+    "pixie_som_accum_f32", "pixie_som_apply_f64",
     "pixie_som_train_f32", "pixie_peer_buffer_bytes", "pixie_som_train_peers_f32",
     "pixie_map_data_to_nodes_host_f32", "pixie_map_data_to_nodes_host_f64",
 ]
@@ -78,6 +79,10 @@ def lib():
         L.pixie_bmu_f32.argtypes = [vp, i64, i32, i64, vp, i32, vp, vp, vp, sz, u32, vp, vp]
         L.pixie_bmu_dist_f64.argtypes = [vp, i64, i32, i64, vp, i32, vp, vp, vp]
         L.pixie_cluster_sums_f32.argtypes = [vp, i64, i32, i64, vp, i32, vp, vp, sz, vp]
+        L.pixie_columns_to_rows_f32.argtypes = [vp, i64, i64, i32, vp, vp, i64, vp]
+        L.pixie_som_online_f64.argtypes = [vp, i64, i32, i64, vp, i32, i32, vp, i64, dbl, dbl, dbl, dbl,
+                                           vp, vp]
+        L.pixie_libc_sample_indices.argtypes = [u32, i64, i64, vp]
         L.pixie_som_accum_f32.argtypes = [vp, i64, i32, i64, vp, i32, i64, i64, vp, vp, sz, u32,
                                           vp, vp]
         L.pixie_som_apply_f64.argtypes = [vp, vp, vp, i32, i32, i32, dbl, dbl, vp]
@@ -90,7 +95,8 @@ def lib():
         L.pixie_som_train_peers_f32.restype = c.c_int
         L.pixie_map_data_to_nodes_host_f32.argtypes = [vp, i32, vp, i64, i32, vp, vp, i32, i64]
         L.pixie_map_data_to_nodes_host_f64.argtypes = [vp, i32, vp, i64, i32, vp, vp, i32, i64]
-        for name in ("pixie_bmu_f32", "pixie_bmu_dist_f64", "pixie_cluster_sums_f32", "pixie_som_accum_f32",
+        for name in ("pixie_bmu_f32", "pixie_bmu_dist_f64", "pixie_cluster_sums_f32", "pixie_columns_to_rows_f32", "pixie_som_online_f64", "pixie_libc_sample_indices",
+    "pixie_som_accum_f32",
                      "pixie_som_apply_f64", "pixie_som_train_f32",
                      "pixie_map_data_to_nodes_host_f32", "pixie_map_data_to_nodes_host_f64"):
             getattr(L, name).restype = c.c_int

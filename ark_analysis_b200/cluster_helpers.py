@@ -138,6 +138,63 @@ class PixelSOMCluster(PixieSOMCluster):
         return labelled
 
 
+    def assign_som_clusters_table(self, table, normalize_data: bool = True):
+        """Arrow-native twin of :meth:`assign_som_clusters` for a FOV read with
+        ``io_utils.read_table``.
+
+        The float64 channel columns go to the device as the Arrow buffers they are; one kernel
+        (``som.columns_to_rows``) normalises, casts and transposes them into the fp32 matrix the
+        BMU kernel streams -- no DataFrame copy, no ``.loc`` gather, no float64 staging matrix.
+        Returns a ``pyarrow.Table`` with the normalised channel columns and the int32
+        ``pixel_som_cluster`` column, i.e. exactly the table the DataFrame path writes; ``None``
+        when the table does not qualify (no rows, nulls, channels that are not float64), in which
+        case the caller takes the DataFrame path."""
+        import pyarrow as pa
+        import torch
+
+        names = table.column_names
+        norm_cols = list(self.norm_data.columns)
+        weights_cols = list(self.weights.columns)
+        if normalize_data:
+            verify_in_list(norm_data_cols=norm_cols, external_data_cols=names)
+        verify_in_list(weights_cols=weights_cols, external_data_cols=names)
+        n = table.num_rows
+        if n == 0 or 'pixel_som_cluster' in names:
+            return None
+        touched = list(dict.fromkeys(weights_cols + (norm_cols if normalize_data else [])))
+        host = {}
+        for col in touched:
+            arr = table.column(col)
+            if arr.type != pa.float64() or arr.null_count:
+                return None
+            host[col] = arr.combine_chunks().to_numpy(zero_copy_only=True) \
+                if arr.num_chunks != 1 else arr.chunk(0).to_numpy(zero_copy_only=True)
+
+        norm_row = self.norm_data.iloc[0]
+        dev = torch.device("cuda", torch.cuda.current_device()) if self.device is None \
+            else torch.device(self.device)
+        C = len(weights_cols)
+        cols = torch.empty((C, n), dtype=torch.float64, device=dev)
+        div = np.ones(C, dtype=np.float64)
+        for j, col in enumerate(weights_cols):
+            cols[j].copy_(torch.from_numpy(host[col]), non_blocking=True)
+            if normalize_data and col in norm_row.index:
+                div[j] = float(norm_row[col])
+        X = som.columns_to_rows(cols, torch.from_numpy(div) if normalize_data else None)
+        W = torch.from_numpy(self.weights.values.astype(np.float64)).to(dev).float().contiguous()
+        labels = som.bmu(X, W).cpu().numpy()
+
+        out = table
+        if normalize_data:
+            for col in norm_cols:
+                i = out.column_names.index(col)
+                out = out.set_column(i, out.schema.field(i),
+                                     pa.array(np.divide(host[col], float(norm_row[col]))))
+        out = out.append_column('pixel_som_cluster', pa.array(labels, type=pa.int32()))
+        self.som_clusters_seen.update(np.unique(labels).tolist())
+        return out
+
+
 class CellSOMCluster(PixieSOMCluster):
     """Cell SOM (reference: cluster_helpers.py:304-416)."""
 

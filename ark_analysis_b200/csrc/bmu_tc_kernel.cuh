@@ -94,6 +94,64 @@ __device__ __forceinline__ float pair_dist2_f32(const uint8_t *xs, const uint8_t
     return (a + b) + (c + d);
 }
 
+// stage 2, two-candidate form: fp32 squared distances of tile row `row` to nodes `na` and `nb` in
+// one walk over the row (the common case: a flagged row has exactly two candidates).  The thread
+// reads ITS OWN row, chunk c at physical chunk c ^ (row & 7), so a quarter-warp (8 consecutive
+// rows) covers all eight bank groups; codebook chunks follow the same logical order.
+__device__ __forceinline__ void duel_dist2_f32(const uint8_t *xs, const uint8_t *ws, int Ntot,
+                                               int nchunks16, int row, int na, int nb, float &da,
+                                               float &db)
+{
+    const uint64_t half2 = pack2(0.5f, 0.5f);
+    uint64_t a0 = 0ull, a1 = 0ull, b0 = 0ull, b1 = 0ull;
+    // rows are 128-byte aligned: OR the row's swizzle key in, XOR the logical chunk index
+    uint32_t xrow = smem_u32(xs) + (uint32_t)row * 128u + ((uint32_t)(row & 7) << 4);
+    uint32_t wa = smem_u32(ws) + (uint32_t)na * 128u + ((uint32_t)(na & 7) << 4);
+    uint32_t wb = smem_u32(ws) + (uint32_t)nb * 128u + ((uint32_t)(nb & 7) << 4);
+    for (int left = nchunks16; left > 0; left -= 8) {
+        if (left >= 8) {
+#pragma unroll
+            for (uint32_t c = 0; c < 8; ++c) {
+                const uint4 xu = lds128(xrow ^ (c << 4));
+                const uint4 au = lds128(wa ^ (c << 4));
+                const uint4 bu = lds128(wb ^ (c << 4));
+                const float4 x = make_float4(__uint_as_float(xu.x), __uint_as_float(xu.y),
+                                             __uint_as_float(xu.z), __uint_as_float(xu.w));
+                dist2_chunk(x, make_float4(__uint_as_float(au.x), __uint_as_float(au.y),
+                                           __uint_as_float(au.z), __uint_as_float(au.w)),
+                            half2, a0, a1);
+                dist2_chunk(x, make_float4(__uint_as_float(bu.x), __uint_as_float(bu.y),
+                                           __uint_as_float(bu.z), __uint_as_float(bu.w)),
+                            half2, b0, b1);
+            }
+        } else {
+            for (uint32_t c = 0; c < (uint32_t)left; ++c) {
+                const uint4 xu = lds128(xrow ^ (c << 4));
+                const uint4 au = lds128(wa ^ (c << 4));
+                const uint4 bu = lds128(wb ^ (c << 4));
+                const float4 x = make_float4(__uint_as_float(xu.x), __uint_as_float(xu.y),
+                                             __uint_as_float(xu.z), __uint_as_float(xu.w));
+                dist2_chunk(x, make_float4(__uint_as_float(au.x), __uint_as_float(au.y),
+                                           __uint_as_float(au.z), __uint_as_float(au.w)),
+                            half2, a0, a1);
+                dist2_chunk(x, make_float4(__uint_as_float(bu.x), __uint_as_float(bu.y),
+                                           __uint_as_float(bu.z), __uint_as_float(bu.w)),
+                            half2, b0, b1);
+            }
+        }
+        xrow += 16384u;
+        wa += (uint32_t)Ntot * 128u;
+        wb += (uint32_t)Ntot * 128u;
+    }
+    float p, q, r, t;
+    unpack2(a0, p, q);
+    unpack2(a1, r, t);
+    da = (p + q) + (r + t);
+    unpack2(b0, p, q);
+    unpack2(b1, r, t);
+    db = (p + q) + (r + t);
+}
+
 // stage 3: the reference's fp64 operation sequence for one (row, node) pair
 // (oracle/pixie_oracle.c nearest_node): tmp = x - w; acc = acc + tmp * tmp (separately rounded),
 // in channel order; d = sqrt(acc).
@@ -588,7 +646,8 @@ bmu_tc_kernel(const __grid_constant__ CUtensorMap tmX, const TcParams p)
             // error model above is relative): such rows simply collect candidates and end in fp64.
             const float E = 0.00415039f * sqrtf(xn2 + 1.0e-30f) * 1.000001f * wmax +
                             3.8147e-6f * wmax2 + 1.0e-30f;
-            const float delta = (w_nonneg && (int32_t)sgn >= 0) ? 1.03125f * E : 2.0f * E;
+            const float delta =
+                ((w_nonneg && (int32_t)sgn >= 0) ? 1.03125f * E : 2.0f * E) * p.delta_scale;
 
             float m_run = __int_as_float(0x7f800000);
             uint32_t mw[NS][NW];
@@ -690,7 +749,53 @@ bmu_tc_kernel(const __grid_constant__ CUtensorMap tmX, const TcParams p)
             }
             bool flagged = finite && nc >= 2 && nc <= kMaxCand;  // kMaxCand <= 15
             const unsigned fmask0 = __ballot_sync(0xffffffffu, flagged);
-            if (fmask0) {
+            // Fast path (warp-uniform): every flagged row of this warp has exactly two candidates.
+            // Each such thread settles its own row -- both fp32 distances in one walk over the row,
+            // fp64 replica only if they are within the fp32 error of each other -- with no pair
+            // list, no compaction and no exchange through shared memory.
+            const bool duel_only = fmask0 != 0u && !p.no_duel && !__any_sync(0xffffffffu, flagged && nc != 2);
+            if (duel_only) {
+                if (flagged) {
+                    int c0 = -1, c1 = -1;  // the two candidates, ascending node index
+#pragma unroll
+                    for (int a = 0; a < NS; ++a)
+#pragma unroll
+                        for (int w = 0; w < NW; ++w) {
+                            const int cw = (SL - 32 * w) < 32 ? (SL - 32 * w) : 32;
+                            const int base = a * SL + 32 * w + cw - 32;
+                            uint32_t m = mw[a][w];
+                            if (m) {
+                                const int lz = __clz(m);
+                                m &= ~(0x80000000u >> lz);
+                                if (c0 < 0) c0 = base + lz; else c1 = base + lz;
+                                if (m) c1 = base + __clz(m);
+                            }
+                        }
+                    if (c0 >= Ntot) c0 = 0;
+                    if (c1 >= Ntot || c1 < 0) c1 = 0;
+                    float d0, d1;
+                    duel_dist2_f32(xs, ws, Ntot, nchunks16, row, c0, c1, d0, d1);
+                    const float best = fminf(d0, d1);
+                    const float bound = best * (1.0f + eps32) + 1.0e-30f;
+                    ++st_flag;
+                    st_pairs += 2;
+                    if (d1 > bound) {
+                        label = c0 + 1;
+                    } else if (d0 > bound) {
+                        label = c1 + 1;
+                    } else {
+                        // stage 3: fp64 replica of the reference loop, ascending node order, strict <
+                        ++st_fp64;
+                        label = kLabelFixup;
+                        if (c0 < pl.K && c1 < pl.K) {
+                            const double e0 = pair_dist_f64(xs, ws, Ntot, pl.C, row, c0);
+                            const double e1 = pair_dist_f64(xs, ws, Ntot, pl.C, row, c1);
+                            label = (e1 < e0 ? c1 : c0) + 1;
+                            if (!(e0 == e0) || !(e1 == e1)) label = kLabelFixup;
+                        }
+                    }
+                }
+            } else if (fmask0) {
                 // warp-local pair list: exclusive prefix of the candidate counts (<= 15, four bits)
                 // of the flagged lanes from four ballots -- no dependent shuffle chain
                 const int cntf = flagged ? nc : 0;

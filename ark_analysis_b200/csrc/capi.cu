@@ -184,6 +184,7 @@ int bmu_tiles(const float *X, int64_t n, int C, int64_t ldX, const float *W, int
         p.partials = fused ? ws.partials : nullptr;
         p.SN = fused ? SN : nullptr;
         p.delta_scale = delta_scale_from_env();
+        p.no_duel = getenv("PIXIE_TC_NODUEL") != nullptr;
         p.plan = plan;
         PX_CUDA(launch_bmu_tc(tm, p, sum_parts(), stream));
         // rows the tensor-core kernel could not settle (NaN/Inf rows, degenerate codebooks): exact
@@ -284,6 +285,43 @@ int pixie_cluster_sums_f32(const float *X, int64_t n, int32_t C, int64_t ldX, co
     return PIXIE_OK;
 }
 
+int pixie_columns_to_rows_f32(const double *cols, int64_t col_stride, int64_t n, int32_t C,
+                              const double *divisor_or_null, float *X, int64_t ldX, void *stream)
+{
+    if (n < 0 || C < 1 || C > 4096 || ldX < C || col_stride < n || !X || (n > 0 && !cols))
+        return PIXIE_ERR_INVALID_ARG;
+    PX_CUDA(launch_columns_to_rows(cols, col_stride, n, C, divisor_or_null, X, ldX,
+                                   num_sms_current_device(),
+                                   reinterpret_cast<cudaStream_t>(stream)));
+    return PIXIE_OK;
+}
+
+int pixie_som_online_f64(const float *X, int64_t n, int32_t C, int64_t ldX, double *W64,
+                         int32_t xdim, int32_t ydim, const int64_t *sample_idx, int64_t niter,
+                         double alpha0, double alpha1, double radius0, double radius1,
+                         long long *iters_done_or_null, void *stream)
+{
+    if (xdim < 1 || ydim < 1 || !W64 || !sample_idx || niter < 1 || n < 1 || !X)
+        return PIXIE_ERR_INVALID_ARG;
+    const int K = xdim * ydim;
+    if (bad_shape(n, C, ldX, K)) return PIXIE_ERR_INVALID_ARG;
+    if (K > 1024 || C > 1024 || som_online_smem_bytes(C, K) > 227u * 1024u)
+        return PIXIE_ERR_UNSUPPORTED;
+    PX_CUDA(launch_som_online(X, n, C, ldX, W64, xdim, ydim, sample_idx, niter, n, alpha0, alpha1,
+                              radius0, radius1, iters_done_or_null,
+                              reinterpret_cast<cudaStream_t>(stream)));
+    return PIXIE_OK;
+}
+
+int pixie_libc_sample_indices(uint32_t seed, int64_t n, int64_t count, int64_t *out_host)
+{
+    if (n < 1 || count < 0 || (count > 0 && !out_host)) return PIXIE_ERR_INVALID_ARG;
+    srand(seed);
+    for (int64_t k = 0; k < count; ++k)
+        out_host[k] = (int64_t)((double)n * ((double)rand() / ((double)RAND_MAX + 1.0)));
+    return PIXIE_OK;
+}
+
 int pixie_som_accum_f32(const float *X, int64_t n, int32_t C, int64_t ldX, const float *W32,
                         int32_t K, int64_t tile_first, int64_t tile_stride, double *SN,
                         void *workspace, size_t ws_bytes, uint32_t flags,
@@ -368,6 +406,7 @@ static int launch_whole_pass(const float *X, int64_t n, int32_t C, int64_t ldX, 
     p.rank = rank;
     p.flag_base = flag_base;
     p.delta_scale = delta_scale_from_env();
+    p.no_duel = getenv("PIXIE_TC_NODUEL") != nullptr;
     for (int r = 0; r < 8; ++r)
         p.peer_buf[r] = (world > 1 && r < world) ? reinterpret_cast<double *>(peer_bufs[r]) : nullptr;
     p.plan = plan;

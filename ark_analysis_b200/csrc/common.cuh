@@ -100,6 +100,7 @@ struct TcParams {
     uint32_t flag_base;    // flags only grow: step st of this launch signals flag_base + st + 1
     double *peer_buf[8];
     float delta_scale;     // 1 in production; tests shrink the candidate window to probe its margin
+    int no_duel;           // 1 = never take the two-candidate fast path (A/B experiments)
     TcPlan plan;
 };
 
@@ -121,6 +122,16 @@ cudaError_t launch_cluster_sums(const float *X, int64_t n, int C, int64_t ldX,
                                 cudaStream_t stream);
 cudaError_t launch_som_apply(double *W64, float *W32, const double *SN, int xdim, int ydim, int C,
                              double sigma, double alpha, cudaStream_t stream);
+
+cudaError_t launch_columns_to_rows(const double *cols, int64_t col_stride, int64_t n, int C,
+                                   const double *divisor, float *X, int64_t ldX, int num_sms,
+                                   cudaStream_t stream);
+
+size_t som_online_smem_bytes(int C, int K);
+cudaError_t launch_som_online(const float *X, int64_t n, int C, int64_t ldX, double *W, int xdim,
+                              int ydim, const int64_t *sample_idx, int64_t niter,
+                              int64_t n_per_pass, double a0, double a1, double r0, double r1,
+                              long long *iters_done, cudaStream_t stream);
 
 // process-wide count of kernels this library has launched (pixie_kernel_launches())
 void count_launch(int n = 1);

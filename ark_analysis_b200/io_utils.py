@@ -30,6 +30,13 @@ def read_table(path, columns=None):
     return _paf.read_table(str(path), columns=columns)
 
 
+def write_table(table, path, compression="uncompressed"):
+    """Write an Arrow table as Feather.  Stale pandas metadata (it may name columns that were
+    dropped or lack the ones appended since) is removed: the Arrow types carry everything
+    ``read_dataframe`` needs."""
+    _paf.write_feather(table.replace_schema_metadata(None), str(path), compression=compression)
+
+
 # ------------------------------------------------------------------------------------------------
 # alpineer.io_utils
 # ------------------------------------------------------------------------------------------------

@@ -56,6 +56,23 @@ def run_pixel_som_assignment(pixel_data_path, pixel_pysom_obj, overwrite, num_pa
     """Label one FOV and write it to ``pixel_data_path + '_temp'``.  Returns ``(fov, status)``,
     status 1 meaning the FOV's file could not be read (it is then skipped and dropped)."""
     fov_path = os.path.join(pixel_data_path, fov + '.feather')
+    temp_path = os.path.join(pixel_data_path + '_temp', fov + '.feather')
+
+    # Arrow-native path (N2): column buffers straight to the device, one normalise + cast +
+    # transpose kernel, the labelled table written back without a DataFrame round trip
+    fast = getattr(pixel_pysom_obj, 'assign_som_clusters_table', None)
+    if fast is not None and num_parallel_pixels > 0:
+        try:
+            table = io_utils.read_table(fov_path)
+        except (ArrowInvalid, OSError, IOError):
+            return fov, 1
+        if overwrite and 'pixel_som_cluster' in table.column_names:
+            table = table.drop_columns(['pixel_som_cluster'])
+        labelled = fast(table, normalize_data=not overwrite)
+        if labelled is not None:
+            io_utils.write_table(labelled, temp_path, compression='uncompressed')
+            return fov, 0
+
     try:
         fov_data = io_utils.read_dataframe(fov_path)
     except (ArrowInvalid, OSError, IOError):
@@ -68,7 +85,6 @@ def run_pixel_som_assignment(pixel_data_path, pixel_pysom_obj, overwrite, num_pa
     fov_data = pixel_pysom_obj.assign_som_clusters(
         fov_data, normalize_data=not overwrite, num_parallel_pixels=num_parallel_pixels)
 
-    temp_path = os.path.join(pixel_data_path + '_temp', fov + '.feather')
     io_utils.write_dataframe(fov_data, temp_path, compression='uncompressed')
     return fov, 0
 

@@ -122,6 +122,39 @@ def to_device_matrix(data, device=None, out=None):
     return view
 
 
+def columns_to_rows(cols, divisor=None, out=None):
+    """N2: turn per-channel float64 column buffers into the device matrix in one kernel.
+
+    ``cols`` is a CUDA float64 tensor [C, n] (row c = the Arrow buffer of channel c; stride(1)
+    must be 1), ``divisor`` an optional [C] float64 tensor (the normalisation row of
+    cluster_helpers.py:244-246).  Returns the [n, C] fp32 view (row pitch a multiple of 4 floats)
+    holding ``float32(cols[c, i] / divisor[c])`` -- bit-identical to casting the reference's
+    normalised float64 table to fp32."""
+    if not isinstance(cols, torch.Tensor) or not cols.is_cuda or cols.dtype != torch.float64 \
+            or cols.dim() != 2 or (cols.shape[1] > 1 and cols.stride(1) != 1):
+        raise PixieError("cols must be a CUDA float64 tensor [C, n] with contiguous columns")
+    C, n = cols.shape
+    dev = cols.device
+    if divisor is not None:
+        divisor = torch.as_tensor(divisor, dtype=torch.float64).to(dev).contiguous()
+        if divisor.numel() != C:
+            raise PixieError("divisor must hold one value per column")
+    ld = (C + 3) // 4 * 4
+    if out is None:
+        out = torch.zeros((max(n, 1), ld), dtype=torch.float32, device=dev)
+    elif out.dtype != torch.float32 or out.dim() != 2 or out.shape[0] < n or out.shape[1] < C \
+            or out.stride(1) != 1 or out.device != dev:
+        raise PixieError("out must be a CUDA float32 matrix with at least [n, C] elements")
+    ld = out.stride(0)
+    if n:
+        with torch.cuda.device(dev):
+            rc = _native.lib().pixie_columns_to_rows_f32(
+                _ptr(cols), cols.stride(0) if C > 1 else max(n, cols.stride(0)), n, C,
+                _ptr(divisor), _ptr(out), ld, _stream(dev))
+        _native.check(rc, "pixie_columns_to_rows_f32")
+    return out[:n, :C]
+
+
 # ------------------------------------------------------------------------------------------------
 # operators
 # ------------------------------------------------------------------------------------------------

@@ -90,6 +90,39 @@ int pixie_cluster_sums_f32(const float *X, int64_t n, int32_t C, int64_t ldX, co
                            int32_t K, double *SN, void *workspace, size_t ws_bytes, void *stream);
 
 /*
+ * N2 -- Feather column buffers -> device matrix.  `cols` holds C float64 columns of n values,
+ * column c starting at cols + c * col_stride (the per-channel Arrow buffers of a FOV file,
+ * pixie_preprocessing.py:172-183, uploaded as they are).  Writes
+ *   X[i, c] = (float)(cols[c][i] / divisor[c])      (divisor NULL: no division)
+ * i.e. normalize_data (cluster_helpers.py:244-246), the column gather (:151-156) and the
+ * float64 -> device fp32 cast in one pass; bit-identical to rounding the reference's normalised
+ * float64 table to fp32.  All pointers are device pointers; divisor is double[C].
+ */
+int pixie_columns_to_rows_f32(const double *cols, int64_t col_stride, int64_t n, int32_t C,
+                              const double *divisor_or_null, float *X, int64_t ldX, void *stream);
+
+/*
+ * Parity mode: pyFlowSOM.som's own ONLINE rule (cluster_helpers.py:106-109; FlowSOM C_SOM as
+ * restated in oracle/pixie_oracle.c) on the device, with the reference's floating-point operation
+ * sequence -- the codebook it returns is bit-identical to that restatement run on the same fp32
+ * inputs.  niter = rlen * n sequential single-sample updates: iteration k takes row
+ * sample_idx[k] (device int64[niter], drawn by the caller -- pixie_libc_sample_indices reproduces
+ * the reference's srand(seed)/rand() stream), moves every node within the shrinking Chebyshev
+ * radius of its BMU towards it by alpha_k, and stops early between passes exactly as C_SOM does.
+ * W64 [K x C] holds the initial codebook on entry and the trained one when the stream drains.
+ * Sequential by nature: one CTA, does not shard (replicas only).  PIXIE_ERR_UNSUPPORTED when
+ * K > 1024, C > 1024 or the fp64 codebook does not fit in shared memory.
+ */
+int pixie_som_online_f64(const float *X, int64_t n, int32_t C, int64_t ldX, double *W64,
+                         int32_t xdim, int32_t ydim, const int64_t *sample_idx, int64_t niter,
+                         double alpha0, double alpha1, double radius0, double radius1,
+                         long long *iters_done_or_null, void *stream);
+/* HOST helper: out_host[k] = (int64)(n * (rand() / (RAND_MAX + 1.0))) after srand(seed) -- the
+ * sample sequence of C_SOM.  Uses (and reseeds) the process-wide libc generator, as the reference
+ * does. */
+int pixie_libc_sample_indices(uint32_t seed, int64_t n, int64_t count, int64_t *out_host);
+
+/*
  * One mini-batch step of the batch SOM (the B200 replacement for pyFlowSOM.som's inner loop,
  * cluster_helpers.py:106-109; algorithm in DESIGN.md section 4).  Visits tiles
  * tile_first, tile_first + tile_stride, ... (< ceil(n / PIXIE_TILE)), finds each row's BMU against
