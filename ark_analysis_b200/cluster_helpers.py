@@ -177,7 +177,10 @@ class PixelSOMCluster(PixieSOMCluster):
         cols = torch.empty((C, n), dtype=torch.float64, device=dev)
         div = np.ones(C, dtype=np.float64)
         for j, col in enumerate(weights_cols):
-            cols[j].copy_(torch.from_numpy(host[col]), non_blocking=True)
+            with warnings.catch_warnings():  # Arrow buffers are read-only; they are only read here
+                warnings.simplefilter("ignore", UserWarning)
+                src = torch.from_numpy(host[col])
+            cols[j].copy_(src, non_blocking=True)
             if normalize_data and col in norm_row.index:
                 div[j] = float(norm_row[col])
         X = som.columns_to_rows(cols, torch.from_numpy(div) if normalize_data else None)

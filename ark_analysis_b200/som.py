@@ -7,6 +7,7 @@ reached through the C ABI of ``include/pixie_b200.h``.  There is no CPU fallback
 device or without the built library these functions raise.
 """
 import ctypes
+import os
 
 import numpy as np
 import torch
@@ -373,12 +374,53 @@ def _default_device():
     return torch.device("cuda", torch.cuda.current_device())
 
 
+def train_som_online(X, W0, xdim, ydim, rlen=1, alpha_range=(0.05, 0.01), radius_range=None,
+                     seed=42):
+    """Parity mode: pyFlowSOM's own ONLINE rule (FlowSOM C_SOM) on a device-resident fp32 matrix,
+    one sequential CTA (``pixie_som_online_f64``).  The sample sequence is the reference's
+    ``srand(seed)`` / ``rand()`` stream.  Returns ``(W64 cuda tensor, iterations executed)``; the
+    codebook is bit-identical to ``oracle.som_online`` on the same fp32-representable inputs."""
+    n, C, ld = _check_x(X)
+    dev = X.device
+    K = xdim * ydim
+    if n < 1:
+        raise PixieError("online training needs at least one row")
+    if radius_range is None:
+        radius_range = default_radius(xdim, ydim)
+    W64 = torch.as_tensor(np.asarray(W0) if not isinstance(W0, torch.Tensor) else W0)
+    W64 = W64.to(device=dev, dtype=torch.float64).contiguous().clone()
+    if tuple(W64.shape) != (K, C):
+        raise PixieError("initial codebook must be [xdim*ydim, C]")
+    niter = int(rlen) * n
+    idx = np.empty(niter, np.int64)
+    L = _native.lib()
+    _native.check(L.pixie_libc_sample_indices(int(seed) & 0xFFFFFFFF, n, niter,
+                                              idx.ctypes.data_as(ctypes.c_void_p)),
+                  "pixie_libc_sample_indices")
+    idx_dev = torch.from_numpy(idx).to(dev)
+    done = torch.zeros(1, dtype=torch.int64, device=dev)
+    with torch.cuda.device(dev):
+        rc = L.pixie_som_online_f64(_ptr(X), n, C, ld, _ptr(W64), xdim, ydim, _ptr(idx_dev), niter,
+                                    float(alpha_range[0]), float(alpha_range[1]),
+                                    float(radius_range[0]), float(radius_range[1]), _ptr(done),
+                                    _stream(dev))
+    _native.check(rc, "pixie_som_online_f64")
+    return W64, int(done.item())
+
+
+# "batch" = the B200 production algorithm (DESIGN.md section 4); "online" = the reference's
+# sequential rule, bit-exact to its restatement (parity mode, one CTA, does not shard)
+DEFAULT_ALGORITHM = os.environ.get("PIXIE_SOM_ALGORITHM", "batch")
+
+
 def som(data, xdim=10, ydim=10, rlen=10, alpha_range=(0.05, 0.01), radius_range=None, seed=None,
-        batches_per_pass=None, device=None):
+        batches_per_pass=None, device=None, algorithm=None):
     """Drop-in for ``pyFlowSOM.som`` as ark calls it (cluster_helpers.py:106-109): trains an
     xdim x ydim SOM on ``data`` [n, C] and returns the codebook as a float64 ndarray [K, C].
 
-    Trains the batch SOM of DESIGN.md section 4 (not pyFlowSOM's sequential online rule)."""
+    ``algorithm="batch"`` (default; ``DEFAULT_ALGORITHM`` / ``PIXIE_SOM_ALGORITHM``) trains the batch
+    SOM of DESIGN.md section 4; ``"online"`` runs pyFlowSOM's sequential online rule itself on the
+    device (``train_som_online``)."""
     device = torch.device(device) if device is not None else _default_device()
     data = np.asarray(data)
     if data.ndim != 2:
@@ -390,6 +432,13 @@ def som(data, xdim=10, ydim=10, rlen=10, alpha_range=(0.05, 0.01), radius_range=
     # the initial codebook is taken from the fp32 device matrix so that a caller holding only the
     # device matrix gets the same result
     W0 = X[torch.as_tensor(idx, device=device)].to(torch.float64)
+    algorithm = algorithm or DEFAULT_ALGORITHM
+    if algorithm == "online":
+        W, _ = train_som_online(X, W0, xdim, ydim, rlen=rlen, alpha_range=alpha_range,
+                                radius_range=radius_range, seed=0 if seed is None else seed)
+        return W.cpu().numpy()
+    if algorithm != "batch":
+        raise ValueError("algorithm must be 'batch' or 'online'")
     W = train_som(X, W0, xdim, ydim, rlen=rlen, alpha_range=alpha_range,
                   radius_range=radius_range, batches_per_pass=batches_per_pass)
     return W.cpu().numpy()

@@ -249,3 +249,25 @@ def test_product_package_never_imports_the_oracle():
                 text = open(os.path.join(dirpath, f)).read()
                 assert "import oracle" not in text and "from oracle" not in text, f
                 assert "pixie_oracle" not in text.replace("oracle/pixie_oracle.c", ""), f
+
+
+def test_libc_sample_indices_reproduce_the_reference_stream():
+    """pixie_libc_sample_indices (host helper of the online parity mode) must draw exactly what
+    C_SOM draws: i = (int)(n * rand() / (RAND_MAX + 1.0)) after srand(seed) -- checked against libc
+    itself and against the oracle's own use of that stream (same seed, same trained codebook is
+    asserted on the GPU in tests/test_train_gpu.py)."""
+    import ctypes
+    from ark_analysis_b200 import _native
+    lib = ctypes.CDLL(_native.build())
+    lib.pixie_libc_sample_indices.argtypes = [ctypes.c_uint32, ctypes.c_int64, ctypes.c_int64,
+                                              ctypes.c_void_p]
+    n, count, seed = 12345, 5000, 42
+    out = np.empty(count, np.int64)
+    assert lib.pixie_libc_sample_indices(seed, n, count, out.ctypes.data_as(ctypes.c_void_p)) == 0
+    libc = ctypes.CDLL("libc.so.6")
+    libc.srand(seed)
+    rand_max = 2147483647
+    want = np.array([int(n * (libc.rand() / (rand_max + 1.0))) for _ in range(count)], np.int64)
+    assert np.array_equal(out, want)
+    assert out.min() >= 0 and out.max() < n
+    assert lib.pixie_libc_sample_indices(seed, 0, 1, out.ctypes.data_as(ctypes.c_void_p)) < 0

@@ -103,3 +103,34 @@ def test_map_quality_is_as_good_as_the_online_reference_rule():
         return oracle.map_data_to_nodes(W, X.astype(np.float64))[1].mean()
     print(f"quantisation error: batch(GPU) {qe(Wb):.5f}  online(oracle) {qe(Wo):.5f}")
     assert qe(Wb) < 1.05 * qe(Wo)
+
+
+# ------------------------------------------------------------------------------------------------
+# parity mode: the reference's own online rule on the device (pixie_som_online_f64)
+# ------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("n,C,xd,yd,rlen", [(3000, 16, 10, 10, 1), (2000, 7, 5, 4, 3),
+                                            (1500, 40, 20, 20, 1), (700, 100, 10, 10, 2),
+                                            (64, 3, 2, 2, 5)])
+def test_online_som_is_bit_identical_to_the_reference_rule(n, C, xd, yd, rlen):
+    """Same fp32-representable inputs, same seed: the device codebook equals the C restatement of
+    pyFlowSOM's C_SOM bit for bit (libc rand() sample stream, fp64 operation order, shrinking
+    radius accumulated step by step, early stop between passes)."""
+    rng = np.random.default_rng(n + C)
+    X = rng.random((n, C)).astype(np.float32)
+    idx = oracle.init_codebook_indices(n, xd * yd, 7)
+    want = oracle.som_online(X.astype(np.float64), xd, yd, rlen=rlen, seed=7, init_idx=idx)
+    Xd = S.to_device_matrix(X)
+    got, iters = S.train_som_online(Xd, X[idx].astype(np.float64), xd, yd, rlen=rlen, seed=7)
+    assert np.array_equal(got.cpu().numpy(), want)
+    assert 1 <= iters <= rlen * n
+
+
+def test_online_som_through_the_pyflowsom_shaped_call():
+    rng = np.random.default_rng(3)
+    X = rng.random((1200, 8)).astype(np.float32)
+    W = S.som(X, xdim=4, ydim=5, rlen=2, seed=11, algorithm="online")
+    idx = oracle.init_codebook_indices(1200, 20, 11)
+    want = oracle.som_online(X.astype(np.float64), 4, 5, rlen=2, seed=11, init_idx=idx)
+    assert W.shape == (20, 8) and np.array_equal(W, want)
+    with pytest.raises(ValueError):
+        S.som(X, xdim=4, ydim=5, algorithm="nope")
