@@ -502,31 +502,40 @@ bmu_tc_kernel(const __grid_constant__ CUtensorMap tmX, const TcParams p)
 
     if (warp == NEPI) {
         // ============================================================ TMA producer
-        if (lane == 0) {
-            // codebook image: linear bulk copies (image is pre-swizzled in global memory); in
-            // whole-pass mode it was rewritten by other CTAs through the generic proxy
-            asm volatile("fence.proxy.async;" ::: "memory");
-            mbar_arrive_expect_tx(bar_w, pl.wimg_bytes);
-            for (uint32_t off = 0; off < pl.wimg_bytes; off += 16384u) {
-                const uint32_t sz = min(16384u, pl.wimg_bytes - off);
-                bulk_load(sbase + off, reinterpret_cast<const uint8_t *>(p.wimg) + off, sz, bar_w);
+        // The whole warp walks the loop (warp-uniform control flow); one elected lane issues.
+        {
+            if (elect_one()) {
+                // codebook image: linear bulk copies (image is pre-swizzled in global memory); in
+                // whole-pass mode it was rewritten by other CTAs through the generic proxy
+                asm volatile("fence.proxy.async;" ::: "memory");
+                mbar_arrive_expect_tx(bar_w, pl.wimg_bytes);
+                for (uint32_t off = 0; off < pl.wimg_bytes; off += 16384u) {
+                    const uint32_t sz = min(16384u, pl.wimg_bytes - off);
+                    bulk_load(sbase + off, reinterpret_cast<const uint8_t *>(p.wimg) + off, sz, bar_w);
+                }
             }
+            __syncwarp();
             uint32_t s = base_seq % (uint32_t)nstage;          // one division per step, then
             uint32_t ph = (base_seq / (uint32_t)nstage) & 1u;  // incremental
             for (uint32_t it = 0; it < cnt; ++it, ph ^= (++s == (uint32_t)nstage), s = s == (uint32_t)nstage ? 0u : s) {
-                mbar_wait(bar_empty + 8u * s, ph ^ 1u);
-                mbar_arrive_expect_tx(bar_full + 8u * s, pl.stage_bytes);
+                mbar_wait_relaxed(bar_empty + 8u * s, ph ^ 1u, p.spin_sleep_ns);
                 const int64_t j = (int64_t)blockIdx.x + (int64_t)it * gridDim.x;
                 const int64_t tile = stp.first + j * stp.stride;
                 const int32_t row0 = (int32_t)(tile * kTile);
-                for (int b = 0; b < pl.nblkX; ++b)
-                    tma_load_2d(sbase + pl.off_x + s * pl.stage_bytes + (uint32_t)b * 16384u,
-                                &tmX, bar_full + 8u * s, b * 32, row0, kEvictFirst);
+                if (elect_one()) {
+                    mbar_arrive_expect_tx(bar_full + 8u * s, pl.stage_bytes);
+                    for (int b = 0; b < pl.nblkX; ++b)
+                        tma_load_2d(sbase + pl.off_x + s * pl.stage_bytes + (uint32_t)b * 16384u,
+                                    &tmX, bar_full + 8u * s, b * 32, row0, kEvictFirst);
+                }
+                __syncwarp();
             }
         }
     } else if (warp == NEPI + 1) {
         // ============================================================ MMA issuer
-        if (lane == 0) {
+        // The whole warp walks the loop and waits on the barriers; one elected lane (always the
+        // same one, as tcgen05.commit requires) issues the MMAs of a tile and their commit.
+        {
             constexpr uint32_t idesc = umma_idesc_tf32(128, (uint32_t)NMMA);
             const uint64_t desc_ones = umma_desc_nosw(sbase + pl.off_ones, 128u, 256u);
             // bias K-step: columns C8..C8+7 of the codebook image
@@ -537,15 +546,16 @@ bmu_tc_kernel(const __grid_constant__ CUtensorMap tmX, const TcParams p)
             uint32_t ph = (base_seq / (uint32_t)nstage) & 1u;
             for (uint32_t it = 0; it < cnt; ++it, ph ^= (++s == (uint32_t)nstage), s = s == (uint32_t)nstage ? 0u : s) {
                 const uint32_t seq = base_seq + it;
-                mbar_wait(bar_full + 8u * s, ph);
+                mbar_wait_relaxed(bar_full + 8u * s, ph, p.spin_sleep_ns);
                 const uint32_t xs_addr = sbase + pl.off_x + s * pl.stage_bytes;
 #pragma unroll
                 for (int c = 0; c < NCH; ++c) {
                     const uint32_t q = seq * (uint32_t)NCH + (uint32_t)c;  // accumulator-chunk counter
                     const uint32_t buf = q % NBUF;
                     const uint32_t bph = (q / NBUF) & 1u;
-                    mbar_wait(bar_tempty + 8u * buf, bph ^ 1u);
+                    mbar_wait_relaxed(bar_tempty + 8u * buf, bph ^ 1u, p.spin_sleep_ns);
                     tc_fence_after();
+                    if (elect_one()) {
                     const uint32_t d_tmem = tmem_base + buf * (uint32_t)NMMA;
                     const uint32_t wrow = (uint32_t)(c * NCHUNK) * 128u;
                     for (int ks = 0; ks < pl.ksteps; ++ks) {
@@ -558,6 +568,8 @@ bmu_tc_kernel(const __grid_constant__ CUtensorMap tmX, const TcParams p)
                         umma_desc_sw128(sbase + bias_blk * wblk_bytes + wrow + bias_off);
                     mma_tf32(d_tmem, desc_ones, dbias, idesc, 1u);
                     mma_commit(bar_tfull + 8u * buf);
+                    }
+                    __syncwarp();
                 }
             }
         }

@@ -101,6 +101,7 @@ struct TcParams {
     double *peer_buf[8];
     float delta_scale;     // 1 in production; tests shrink the candidate window to probe its margin
     int no_duel;           // 1 = never take the two-candidate fast path (A/B experiments)
+    uint32_t spin_sleep_ns;  // sleep between mbarrier probes of the producer / MMA-issuer warps
     TcPlan plan;
 };
 

@@ -12,7 +12,7 @@ import bench  # noqa: E402  (data generator of the benchmark)
 from ark_analysis_b200 import som as S  # noqa: E402
 
 cfg = {k: os.environ.get(k, "-") for k in
-       ("PIXIE_TC_NODUEL", "PIXIE_TC_STAGES", "PIXIE_DELTA_SCALE")}
+       ("PIXIE_TC_SPIN_SLEEP", "PIXIE_TC_STAGES", "PIXIE_DELTA_SCALE")}
 tag = " ".join(f"{k[6:]}={v}" for k, v in cfg.items())
 
 
