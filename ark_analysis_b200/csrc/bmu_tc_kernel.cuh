@@ -518,7 +518,7 @@ bmu_tc_kernel(const __grid_constant__ CUtensorMap tmX, const TcParams p)
             uint32_t s = base_seq % (uint32_t)nstage;          // one division per step, then
             uint32_t ph = (base_seq / (uint32_t)nstage) & 1u;  // incremental
             for (uint32_t it = 0; it < cnt; ++it, ph ^= (++s == (uint32_t)nstage), s = s == (uint32_t)nstage ? 0u : s) {
-                mbar_wait_relaxed(bar_empty + 8u * s, ph ^ 1u, p.spin_sleep_ns);
+                mbar_wait(bar_empty + 8u * s, ph ^ 1u);
                 const int64_t j = (int64_t)blockIdx.x + (int64_t)it * gridDim.x;
                 const int64_t tile = stp.first + j * stp.stride;
                 const int32_t row0 = (int32_t)(tile * kTile);
@@ -546,14 +546,14 @@ bmu_tc_kernel(const __grid_constant__ CUtensorMap tmX, const TcParams p)
             uint32_t ph = (base_seq / (uint32_t)nstage) & 1u;
             for (uint32_t it = 0; it < cnt; ++it, ph ^= (++s == (uint32_t)nstage), s = s == (uint32_t)nstage ? 0u : s) {
                 const uint32_t seq = base_seq + it;
-                mbar_wait_relaxed(bar_full + 8u * s, ph, p.spin_sleep_ns);
+                mbar_wait(bar_full + 8u * s, ph);
                 const uint32_t xs_addr = sbase + pl.off_x + s * pl.stage_bytes;
 #pragma unroll
                 for (int c = 0; c < NCH; ++c) {
                     const uint32_t q = seq * (uint32_t)NCH + (uint32_t)c;  // accumulator-chunk counter
                     const uint32_t buf = q % NBUF;
                     const uint32_t bph = (q / NBUF) & 1u;
-                    mbar_wait_relaxed(bar_tempty + 8u * buf, bph ^ 1u, p.spin_sleep_ns);
+                    mbar_wait(bar_tempty + 8u * buf, bph ^ 1u);
                     tc_fence_after();
                     if (elect_one()) {
                     const uint32_t d_tmem = tmem_base + buf * (uint32_t)NMMA;
@@ -765,7 +765,7 @@ bmu_tc_kernel(const __grid_constant__ CUtensorMap tmX, const TcParams p)
             // Each such thread settles its own row -- both fp32 distances in one walk over the row,
             // fp64 replica only if they are within the fp32 error of each other -- with no pair
             // list, no compaction and no exchange through shared memory.
-            const bool duel_only = fmask0 != 0u && !p.no_duel && !__any_sync(0xffffffffu, flagged && nc != 2);
+            const bool duel_only = fmask0 != 0u && !__any_sync(0xffffffffu, flagged && nc != 2);
             if (duel_only) {
                 if (flagged) {
                     int c0 = -1, c1 = -1;  // the two candidates, ascending node index

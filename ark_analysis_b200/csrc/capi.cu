@@ -111,14 +111,6 @@ float delta_scale_from_env()
     return (f > 0.f && f <= 64.f) ? f : 1.0f;
 }
 
-uint32_t spin_sleep_from_env()
-{
-    const char *v = getenv("PIXIE_TC_SPIN_SLEEP");
-    if (!v || !v[0]) return 0u;
-    const int f = atoi(v);
-    return (f >= 0 && f <= 10000) ? (uint32_t)f : 0u;
-}
-
 // ---- workspace carve-up
 struct Workspace {
     float *wimg;
@@ -192,8 +184,6 @@ int bmu_tiles(const float *X, int64_t n, int C, int64_t ldX, const float *W, int
         p.partials = fused ? ws.partials : nullptr;
         p.SN = fused ? SN : nullptr;
         p.delta_scale = delta_scale_from_env();
-        p.no_duel = getenv("PIXIE_TC_NODUEL") != nullptr;
-        p.spin_sleep_ns = spin_sleep_from_env();
         p.plan = plan;
         PX_CUDA(launch_bmu_tc(tm, p, sum_parts(), stream));
         // rows the tensor-core kernel could not settle (NaN/Inf rows, degenerate codebooks): exact
@@ -415,8 +405,6 @@ static int launch_whole_pass(const float *X, int64_t n, int32_t C, int64_t ldX, 
     p.rank = rank;
     p.flag_base = flag_base;
     p.delta_scale = delta_scale_from_env();
-    p.no_duel = getenv("PIXIE_TC_NODUEL") != nullptr;
-    p.spin_sleep_ns = spin_sleep_from_env();
     for (int r = 0; r < 8; ++r)
         p.peer_buf[r] = (world > 1 && r < world) ? reinterpret_cast<double *>(peer_bufs[r]) : nullptr;
     p.plan = plan;

@@ -100,8 +100,6 @@ struct TcParams {
     uint32_t flag_base;    // flags only grow: step st of this launch signals flag_base + st + 1
     double *peer_buf[8];
     float delta_scale;     // 1 in production; tests shrink the candidate window to probe its margin
-    int no_duel;           // 1 = never take the two-candidate fast path (A/B experiments)
-    uint32_t spin_sleep_ns;  // sleep between mbarrier probes of the producer / MMA-issuer warps
     TcPlan plan;
 };
 

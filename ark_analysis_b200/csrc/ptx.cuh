@@ -70,24 +70,6 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity)
     }
 }
 
-// Same for the single-lane producer / MMA-issuer warps: they wait most of the time, and a tight
-// probe loop competes with the epilogue warps of their scheduler for issue slots and for the ALU
-// pipe.  A short sleep between probes keeps them off the scheduler; their wake-up latency is hidden
-// by the depth of the stage / accumulator pipelines.
-__device__ __forceinline__ void mbar_wait_relaxed(uint32_t bar, uint32_t parity, uint32_t sleep_ns)
-{
-    uint32_t spins = 0;
-    uint64_t t0 = 0;
-    while (!mbar_try_wait(bar, parity)) {
-        if (sleep_ns) __nanosleep(sleep_ns);
-        if ((++spins & 1023u) == 0u) {
-            const uint64_t now = global_timer_ns();
-            if (t0 == 0) t0 = now;
-            if (now - t0 > 2000000000ull) __trap();
-        }
-    }
-}
-
 // One thread of a CONVERGED warp: true in exactly one lane (the same one every time).  The
 // single-thread instructions (TMA, tcgen05.mma / commit) are issued under this predicate from
 // warp-uniform control flow; under a plain `if (lane == 0)` region the compiler serialises every

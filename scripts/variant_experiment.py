@@ -1,5 +1,5 @@
 """Assign kernel variants: parity, candidate-window margin and timing for one configuration
-(environment knobs PIXIE_TC_NODUEL / PIXIE_TC_STAGES / PIXIE_DELTA_SCALE are read by the library).
+(environment knobs PIXIE_TC_STAGES / PIXIE_DELTA_SCALE are read by the library).
 Usage: python scripts/variant_experiment.py <parity|timing|timingU|margin> [C] [K] [nfov]"""
 import os
 import sys
@@ -12,7 +12,7 @@ import bench  # noqa: E402  (data generator of the benchmark)
 from ark_analysis_b200 import som as S  # noqa: E402
 
 cfg = {k: os.environ.get(k, "-") for k in
-       ("PIXIE_TC_SPIN_SLEEP", "PIXIE_TC_STAGES", "PIXIE_DELTA_SCALE")}
+       ("PIXIE_TC_STAGES", "PIXIE_DELTA_SCALE")}
 tag = " ".join(f"{k[6:]}={v}" for k, v in cfg.items())
 
 

@@ -268,3 +268,22 @@ def test_full_size_properties_cfg4_cells():
 def test_full_size_properties_cfg3_shard_slice():
     """BASELINE.json config 3 shape (40 channels, 20x20 SOM) on 8 of a GPU's 62 FOVs of 2048^2."""
     _full_size_properties(8 * 2048 * 2048, 40, 400, (0, 16_000_000, 33_000_000))
+
+
+def test_candidate_window_has_margin(monkeypatch):
+    """The tensor-core candidate window is a PROVEN bound on the tf32 score error; this probes how
+    much room it has: with the window shrunk to a quarter (PIXIE_DELTA_SCALE, a test knob read by
+    the library) far fewer rows reach the recheck and the labels are still bit-identical to the
+    exact kernel -- i.e. the bound is not the kind that only just holds."""
+    X = S.to_device_matrix(pixie_like(1 << 20, 32, seed=3))
+    W = X[:100].contiguous()
+    ref = S.bmu(X, W, flags=S.FLAG_FORCE_EXACT)
+    flagged = []
+    for scale in ("1", "0.25"):
+        monkeypatch.setenv("PIXIE_DELTA_SCALE", scale)
+        stats = torch.zeros(S.NSTATS, dtype=torch.int64, device="cuda")
+        lab = S.bmu(X, W, flags=S.FLAG_FORCE_TC, stats=stats)
+        torch.cuda.synchronize()
+        assert torch.equal(lab, ref)
+        flagged.append(int(stats[0]))  # PIXIE_STAT_ROWS_FLAGGED
+    assert flagged[1] < 0.6 * flagged[0]
