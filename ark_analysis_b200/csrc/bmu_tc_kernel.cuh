@@ -740,6 +740,17 @@ bmu_tc_kernel(const __grid_constant__ CUtensorMap tmX, const TcParams p)
                 }
             }
 
+            if constexpr (NCH == 2 && !ACC) {
+                // Two chunks per tile share their TMEM buffers between the two groups, so the
+                // waits above are only alias-free if no warp of this group runs a whole tile ahead
+                // of another: a warp that reached tile seq + 2 while a sibling had not yet drained
+                // tile seq would find `tempty` two phases behind, fall through both parity waits
+                // and read tile seq's scores again (seen with >= 4 X stages: 32 wrong labels, then
+                // a dead-locked barrier).  Once all four warps have drained this tile they may
+                // drift apart again for the recheck.  (Train mode syncs the group per tile anyway.)
+                bar_sync(1u + (uint32_t)g, 128);
+            }
+
             // ---- resolve
             int nc = 0;
 #pragma unroll

@@ -74,6 +74,31 @@ def test_trained_codebooks_bit_exact(C, K):
         assert int(stats[S._native.STAT_ROWS_FLAGGED]) > 0  # the recheck path was taken
 
 
+@pytest.mark.parametrize("C,K", [(16, 400), (32, 400), (24, 324), (40, 400)])
+def test_two_chunk_variants_with_a_deep_pipeline(C, K):
+    """K > 256 runs two accumulator chunks per tile whose TMEM buffers are shared by the two
+    epilogue groups; with C <= 32 there is room for 6-8 X stages, and a warp that ran a tile ahead
+    of its group used to fall through an aliased parity wait (32 wrong labels, then a trap).  The
+    race needed many tiles per CTA and a trained map (uneven recheck work): 2^21 rows, three
+    launches, every label compared with the exact fp64 kernel."""
+    n = 1 << 21
+    g = torch.Generator(device="cuda").manual_seed(C * 7 + K)
+    X = torch.rand((n, C), device="cuda", generator=g)
+    xd = int(round(np.sqrt(K)))
+    idx = np.random.default_rng(42).choice(n, K, replace=False)
+    W = S.train_som(X[:1 << 20], X[torch.from_numpy(idx).cuda()].double(), xd, K // xd,
+                    rlen=1).float().contiguous()
+    ref = S.bmu(X, W, flags=S.FLAG_FORCE_EXACT)
+    for _ in range(3):
+        lab = S.bmu(X, W, flags=S.FLAG_FORCE_TC)
+        torch.cuda.synchronize()
+        assert int((lab != ref).sum()) == 0
+    # the exact kernel itself against the oracle on a slice
+    sl = slice(12345, 12345 + 4000)
+    o, _ = oracle.map_data_to_nodes_f32(W.cpu().numpy(), X[sl].cpu().numpy())
+    np.testing.assert_array_equal(ref[sl].cpu().numpy(), o)
+
+
 def test_exact_kernel_and_unsupported_shapes_fall_back():
     X = data("U", 3000, 130)  # C > 128: not a tensor-core shape
     W = X[:20].copy()
