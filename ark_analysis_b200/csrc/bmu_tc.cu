@@ -89,12 +89,12 @@ TcPlan make_tc_plan(int C, int K, bool acc)
         p.wimg_bytes = (uint32_t)p.nblkW * (uint32_t)p.Ntot * 128u;
         p.off_ones = p.wimg_bytes;
         p.off_x = p.off_ones + 4096u;
-        // fused accumulation: one fp32 table per epilogue group + the tile's labels per group;
-        // the (C+1) columns are split over the 4 warps of a group, 32 lanes each
-        if (acc && (C + 1 + 3) / 4 > 32) continue;
+        // fused accumulation: one fp32 table per epilogue group + the group's sort scratch
+        if (acc && C + 1 > 128) continue;  // the side-buffer merge: one thread of the group per column
+        const uint32_t sort_bytes = sort_layout(C, K).bytes;
         const uint32_t acc_bytes =
             acc ? ((uint32_t)v.NG * (uint32_t)K * (uint32_t)(C + 1) * 4u + 15u) / 16u * 16u +
-                      (uint32_t)v.NG * 512u
+                      (uint32_t)v.NG * sort_bytes
                 : 0u;
         const uint32_t pair_cap = acc ? kWarpPairCapAcc : kWarpPairCap;
         const uint32_t scratch = (uint32_t)kBarBlock + (uint32_t)(4 * v.NG) * pair_cap * 8u + acc_bytes;
@@ -110,7 +110,8 @@ TcPlan make_tc_plan(int C, int K, bool acc)
         p.off_pairs = p.off_bar + (uint32_t)kBarBlock;
         p.pair_cap = (int)pair_cap;
         p.off_acc = p.off_pairs + (uint32_t)(4 * v.NG) * pair_cap * 8u;
-        p.off_lab = p.off_acc + (acc_bytes ? acc_bytes - (uint32_t)v.NG * 512u : 0u);
+        p.off_lab = p.off_acc + (acc_bytes ? acc_bytes - (uint32_t)v.NG * sort_bytes : 0u);
+        p.sort_stride = sort_bytes;
         p.acc = acc ? 1 : 0;
         p.smem_bytes = p.off_acc + acc_bytes + 1024u;
         p.ok = true;

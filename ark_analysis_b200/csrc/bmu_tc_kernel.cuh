@@ -417,6 +417,135 @@ __device__ __noinline__ void step_update(const TcParams &p, int st, uint8_t *sme
 }
 
 // ------------------------------------------------------------------------------------------------
+// train mode: add one tile's rows to the epilogue group's private K x (C+1) table (sums + counts).
+// Called by the 128 threads of group g once the tile's labels are known (L = label bin of this
+// thread's row, K = "skip": padding and unassignable rows).  Deterministic, no atomics:
+//   1. stable counting sort of the 128 rows by label: rank inside the warp from match.any, one
+//      histogram byte per (warp, label), every warp scans the bins itself (32 lanes x nbl bins);
+//   2. warp w walks sorted positions [32w, 32w+32) with lanes = channels: the rows of a node are
+//      contiguous, so a node's sum is a register accumulation over independent shared-memory loads
+//      (the walk that used to be a 128-long chain of dependent read-modify-writes on the table);
+//      each finished segment is one read-modify-write on cells no other warp touches -- except the
+//      warp's FIRST segment, whose node may continue from the previous warp's range: that one goes
+//      to a side buffer;
+//   3. after a group barrier the side buffers are added in warp order.
+// Sum order inside a tile: ascending row inside a warp range, warp ranges in order.
+// ------------------------------------------------------------------------------------------------
+static __device__ __noinline__ void tile_accumulate_sorted(uint8_t *smem, const uint8_t *xs,
+                                                           uint32_t off_acc, uint32_t off_sort, int K,
+                                                           int C, int nblkX, int g, int quad,
+                                                           int lane, int L)
+{
+    const SortLayout sl = sort_layout(C, K);
+    uint8_t *base = smem + off_sort;
+    uint32_t *hist32 = reinterpret_cast<uint32_t *>(base);
+    uint8_t *wbase = base + sl.off_wbase + (uint32_t)quad * sl.bins;
+    uint8_t *order = base + sl.off_order;
+    uint16_t *slab = reinterpret_cast<uint16_t *>(base + sl.off_slab);
+    float *side = reinterpret_cast<float *>(base + sl.off_side);
+    int *side_lab = reinterpret_cast<int *>(base + sl.off_sidelab);
+    const int acc_ld = C + 1;
+    float *tab = reinterpret_cast<float *>(smem + off_acc) + (size_t)g * K * acc_ld;
+    const uint32_t bar = 1u + (uint32_t)g;
+
+    // 1a. rows of this warp with my label; the lowest such lane publishes their count
+    const unsigned peers = __match_any_sync(0xffffffffu, L);
+    const int rk = __popc(peers & ((1u << lane) - 1u));
+    if (rk == 0) base[4 * L + quad] = (uint8_t)__popc(peers);
+    bar_sync(bar, 128);
+    // 1b. every warp scans all bins: lane l owns bins [l * nbl, (l + 1) * nbl)
+    {
+        const uint32_t *hp = hist32 + (uint32_t)lane * sl.nbl;
+        uint32_t run = 0;
+        for (uint32_t i = 0; i < sl.nbl; ++i) run += __dp4a(hp[i], 0x01010101u, 0u);
+        uint32_t inc = run;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const uint32_t t = __shfl_up_sync(0xffffffffu, inc, o);
+            if (lane >= o) inc += t;
+        }
+        uint32_t pos0 = inc - run;
+        const uint32_t below = 0x01010101u & ((1u << (8 * quad)) - 1u);  // warps before this one
+        uint8_t *wp = wbase + (uint32_t)lane * sl.nbl;
+        for (uint32_t i = 0; i < sl.nbl; ++i) {
+            const uint32_t w = hp[i];
+            wp[i] = (uint8_t)(pos0 + __dp4a(w, below, 0u));
+            pos0 += __dp4a(w, 0x01010101u, 0u);
+        }
+    }
+    __syncwarp();
+    {
+        const int pos = (int)wbase[L] + rk;
+        order[pos] = (uint8_t)(quad * 32 + lane);
+        slab[pos] = (uint16_t)L;
+    }
+    bar_sync(bar, 128);
+    if (rk == 0) base[4 * L + quad] = 0;  // histograms are zero again for the next tile
+
+    // 2. segment walk
+    const int my_row = order[quad * 32 + lane];
+    const int my_L = slab[quad * 32 + lane];
+    if (lane == 0) side_lab[quad] = -1;
+    for (int cb = 0; cb < nblkX; ++cb) {
+        const int ch = cb * 32 + lane;
+        const uint8_t *xb = xs + (uint32_t)cb * 16384u + (uint32_t)(lane & 3) * 4u;
+        const uint32_t chunk = (uint32_t)lane >> 2;
+        float a = 0.f;
+        int curL = __shfl_sync(0xffffffffu, my_L, 0), seg_len = 0;
+        bool first = true;
+        auto flush = [&]() {
+            if (curL < K) {
+                if (first) {
+                    if (ch < C) side[quad * acc_ld + ch] = a;
+                    if (cb == 0 && lane == 0) {
+                        side[quad * acc_ld + C] = (float)seg_len;
+                        side_lab[quad] = curL;
+                    }
+                } else {
+                    if (ch < C) tab[curL * acc_ld + ch] += a;
+                    if (cb == 0 && lane == 0) tab[curL * acc_ld + C] += (float)seg_len;
+                }
+            }
+        };
+#pragma unroll 1
+        for (int i0 = 0; i0 < 32; i0 += 16) {
+            float v[16];
+#pragma unroll
+            for (int u = 0; u < 16; ++u) {
+                const uint32_t r = (uint32_t)__shfl_sync(0xffffffffu, my_row, i0 + u);
+                v[u] = *reinterpret_cast<const float *>(xb + r * 128u + ((chunk ^ (r & 7u)) << 4));
+            }
+#pragma unroll
+            for (int u = 0; u < 16; ++u) {
+                const int Lu = __shfl_sync(0xffffffffu, my_L, i0 + u);
+                if (Lu != curL) {  // warp-uniform
+                    flush();
+                    first = false;
+                    curL = Lu;
+                    a = 0.f;
+                    seg_len = 0;
+                }
+                if (Lu < K) {
+                    a += v[u];
+                    ++seg_len;
+                }
+            }
+        }
+        if (seg_len > 0) flush();
+    }
+    bar_sync(bar, 128);
+    // 3. side buffers, warp order; thread t of the group owns column t of the table
+    const int col = quad * 32 + lane;
+    if (col <= C) {
+#pragma unroll
+        for (int w = 0; w < 4; ++w) {
+            const int sL = side_lab[w];
+            if (sL >= 0) tab[sL * acc_ld + col] += side[w * acc_ld + col];
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
 // the kernel
 // ------------------------------------------------------------------------------------------------
 template <int SL, int SPC, int NCH, int NG, bool ACC>
@@ -479,6 +608,9 @@ bmu_tc_kernel(const __grid_constant__ CUtensorMap tmX, const TcParams p)
     if constexpr (ACC) {
         float *a = reinterpret_cast<float *>(smem + pl.off_acc);
         for (int i = threadIdx.x; i < NG * pl.K * (pl.C + 1); i += blockDim.x) a[i] = 0.f;
+        // the sort scratch keeps its histograms zero between tiles
+        uint32_t *sc = reinterpret_cast<uint32_t *>(smem + pl.off_lab);
+        for (uint32_t i = threadIdx.x; i < (uint32_t)NG * pl.sort_stride / 4u; i += blockDim.x) sc[i] = 0u;
     }
     fence_proxy_async();  // the ones tile is read by the tensor core (async proxy)
     tc_fence_before();
@@ -595,10 +727,6 @@ bmu_tc_kernel(const __grid_constant__ CUtensorMap tmX, const TcParams p)
             ((!ACC || st == 0) ? p.ctl->w_has_negative : p.ctl->pp_w_has_negative[st & 1]) == 0;
         // fused accumulation (train mode)
         constexpr bool do_acc = ACC;
-        const int acc_ld = pl.C + 1;
-        const int acc_cq = (pl.C + 1 + 3) / 4;  // columns per warp of the group (<= 32)
-        float *acc_tab = reinterpret_cast<float *>(smem + pl.off_acc) + (size_t)g * pl.K * acc_ld;
-        int *acc_lab = reinterpret_cast<int *>(smem + pl.off_lab) + g * kTile;
 
         // this group's tiles of the step: local indices it with (base_seq + it) % NG == g
         const uint32_t it0 = ((uint32_t)g + (uint32_t)NG - base_seq % (uint32_t)NG) % (uint32_t)NG;
@@ -949,57 +1077,10 @@ bmu_tc_kernel(const __grid_constant__ CUtensorMap tmX, const TcParams p)
                 }
             }
             if constexpr (do_acc) {
-                // ---- fused per-node sums: the group's 4 warps split the C+1 columns (channels +
-                // count); each warp walks the tile's 128 rows IN ROW ORDER with plain
-                // read-modify-writes on the group's private table (no atomics: a column belongs to
-                // one lane), so the sums are deterministic.
-                acc_lab[row] = (grow < p.n && label > 0) ? label - 1 : -1;
-                bar_sync(1u + (uint32_t)g, 128);
-                const int col = quad * acc_cq + lane;  // column of the K x (C+1) table
-                if (lane < acc_cq && col <= pl.C) {
-                    const bool is_cnt = col == pl.C;
-                    // byte offset of channel `col` inside a tile row, before the row swizzle
-                    const uint32_t blk_off = (uint32_t)(col >> 5) * 16384u;
-                    const uint32_t chunk = (uint32_t)(col & 31) >> 2, within = (uint32_t)(col & 3) * 4u;
-                    const uint8_t *xb = xs + blk_off + within;
-                    float *tab = acc_tab + col;
-                    // Four rows at a time: their labels are warp-uniform, so rows of the same node
-                    // are first merged in registers (earliest row keeps the sum), which leaves up to
-                    // four read-modify-writes on DISTINCT cells -- independent, hence pipelined,
-                    // instead of a 128-long chain of dependent shared-memory round trips.
-                    for (int r = 0; r < kTile; r += 4) {
-                        const int4 lb = *reinterpret_cast<const int4 *>(acc_lab + r);
-                        int l0 = lb.x, l1 = lb.y, l2 = lb.z, l3 = lb.w;
-                        float v0, v1, v2, v3;
-                        if (is_cnt) {
-                            v0 = v1 = v2 = v3 = 1.0f;
-                        } else {
-                            const uint8_t *xr = xb + (uint32_t)r * 128u;
-                            // rows r..r+3 share r & 4; their swizzle keys are (r & 7) + 0..3
-                            v0 = *reinterpret_cast<const float *>(xr + ((chunk ^ ((uint32_t)(r + 0) & 7u)) << 4));
-                            v1 = *reinterpret_cast<const float *>(xr + 128u + ((chunk ^ ((uint32_t)(r + 1) & 7u)) << 4));
-                            v2 = *reinterpret_cast<const float *>(xr + 256u + ((chunk ^ ((uint32_t)(r + 2) & 7u)) << 4));
-                            v3 = *reinterpret_cast<const float *>(xr + 384u + ((chunk ^ ((uint32_t)(r + 3) & 7u)) << 4));
-                        }
-                        if (l1 == l0) { v0 += v1; l1 = -1; }
-                        if (l2 == l0) { v0 += v2; l2 = -1; }
-                        if (l3 == l0) { v0 += v3; l3 = -1; }
-                        if (l2 == l1) { v1 += v2; l2 = -1; }
-                        if (l3 == l1) { v1 += v3; l3 = -1; }
-                        if (l3 == l2) { v2 += v3; l3 = -1; }
-                        // (merging two rows that are both skipped, label -1, is harmless)
-                        float *c0 = tab + (l0 < 0 ? 0 : l0) * acc_ld;
-                        float *c1 = tab + (l1 < 0 ? 0 : l1) * acc_ld;
-                        float *c2 = tab + (l2 < 0 ? 0 : l2) * acc_ld;
-                        float *c3 = tab + (l3 < 0 ? 0 : l3) * acc_ld;
-                        const float t0 = *c0, t1 = *c1, t2 = *c2, t3 = *c3;
-                        if (l0 >= 0) *c0 = t0 + v0;
-                        if (l1 >= 0) *c1 = t1 + v1;
-                        if (l2 >= 0) *c2 = t2 + v2;
-                        if (l3 >= 0) *c3 = t3 + v3;
-                    }
-                }
-                bar_sync(1u + (uint32_t)g, 128);  // acc_lab is rewritten by the next tile
+                // ---- fused per-node sums (deterministic, no atomics): see tile_accumulate_sorted
+                tile_accumulate_sorted(smem, xs, pl.off_acc, pl.off_lab + (uint32_t)g * pl.sort_stride,
+                                       pl.K, pl.C, pl.nblkX, g, quad, lane,
+                                       (grow < p.n && label > 0) ? label - 1 : pl.K);
             }
             // all reads of this X stage by this warp are done
             __syncwarp();

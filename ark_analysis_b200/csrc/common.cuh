@@ -55,11 +55,38 @@ struct TcPlan {
     int nstage;  // X tile pipeline depth (multiple of NG)
     uint32_t stage_bytes, wimg_bytes;
     uint32_t off_ones, off_x, off_bar, off_pairs;
-    uint32_t off_acc, off_lab;  // fused accumulation (train mode): NG x K x (C+1) fp32, NG x 128 int
+    uint32_t off_acc, off_lab;  // fused accumulation (train mode): NG x K x (C+1) fp32 tables, then
+                                // NG x sort_stride bytes of per-group sort scratch (SortLayout)
+    uint32_t sort_stride;
     int acc;                    // 1 = this plan has room for the fused accumulation
     int pair_cap;               // pair-list capacity per epilogue warp
     uint32_t smem_bytes;  // dynamic shared memory to request (includes 1 KiB alignment slack)
 };
+
+// Per-group scratch of the fused accumulation (train mode): the tile's 128 rows are counting-sorted
+// by label so that the rows of a node are contiguous and their sum is a register accumulation.
+//   hist32  uint32[bins]     byte w of word b = rows of warp w labelled b (bin K = rows to skip)
+//   wbase   uint8 [4][bins]  sorted position of the first row of warp w labelled b
+//   order   uint8 [128]      sorted position -> tile row
+//   slab    uint16[128]      sorted position -> label bin
+//   side    float [4][C+1]   sum (and count) of a warp's FIRST segment: its node may continue from
+//   side_lab int[4]          the previous warp's range, so it is merged after a group barrier
+struct SortLayout {
+    uint32_t nbl, bins, off_wbase, off_order, off_slab, off_side, off_sidelab, bytes;
+};
+__host__ __device__ inline SortLayout sort_layout(int C, int K)
+{
+    SortLayout s;
+    s.nbl = ((uint32_t)K + 1u + 31u) / 32u;  // bins scanned per lane
+    s.bins = 32u * s.nbl;
+    s.off_wbase = s.bins * 4u;
+    s.off_order = s.off_wbase + 4u * s.bins;
+    s.off_slab = s.off_order + 128u;
+    s.off_side = s.off_slab + 256u;
+    s.off_sidelab = s.off_side + (4u * (uint32_t)(C + 1) * 4u + 15u) / 16u * 16u;
+    s.bytes = s.off_sidelab + 16u;
+    return s;
+}
 
 // acc = true: also reserve per-group fp32 accumulators for the fused per-node sums (train mode).
 // PIXIE_TC_STAGES (environment, experiments only) caps the pipeline depth.
