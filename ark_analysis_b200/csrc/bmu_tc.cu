@@ -70,7 +70,7 @@ TcPlan make_tc_plan(int C, int K, bool acc)
         p.C8 = (C + 7) / 8 * 8;
         p.ksteps = p.C8 / 8;
         p.nblkX = (C + 31) / 32;
-        p.nblkW = (p.C8 + 8 + 31) / 32;
+        p.nblkW = (p.C8 + 31) / 32;
         p.SL = v.SL;
         p.spc = v.spc;
         p.NCH = v.NCH;
@@ -86,8 +86,9 @@ TcPlan make_tc_plan(int C, int K, bool acc)
         p.tmem_cols = 32;
         while (p.tmem_cols < need) p.tmem_cols *= 2;
         p.stage_bytes = (uint32_t)p.nblkX * 16384u;
-        p.wimg_bytes = (uint32_t)p.nblkW * (uint32_t)p.Ntot * 128u;
-        p.off_ones = p.wimg_bytes;
+        p.off_bias = (uint32_t)p.nblkW * (uint32_t)p.Ntot * 128u;
+        p.wimg_bytes = p.off_bias + (uint32_t)p.Ntot * 32u;
+        p.off_ones = (p.wimg_bytes + 1023u) / 1024u * 1024u;
         p.off_x = p.off_ones + 4096u;
         // fused accumulation: one fp32 table per epilogue group + the group's sort scratch
         if (acc && C + 1 > 128) continue;  // the side-buffer merge: one thread of the group per column
@@ -105,6 +106,8 @@ TcPlan make_tc_plan(int C, int K, bool acc)
         if (p.nstage > cap_stages && cap_stages >= v.NG) p.nstage = cap_stages;
         // a multiple of NG: stage (it % nstage) is then always consumed by the same epilogue group
         // (it % NG), so no consumer can reach a full-barrier wait a phase early (parity aliasing).
+        // (Measured: a free stage count -- 7 instead of 4 stages in train mode, made safe by an
+        // extra wait for the stage's previous release -- bought nothing and cost assign 1.7 %.)
         p.nstage = p.nstage / v.NG * v.NG;
         p.off_bar = p.off_x + (uint32_t)p.nstage * p.stage_bytes;
         p.off_pairs = p.off_bar + (uint32_t)kBarBlock;
@@ -130,8 +133,8 @@ TcPlan make_tc_plan(int C, int K, bool acc)
 // ------------------------------------------------------------------------------------------------
 // one warp per codebook row; lanes stride over the image columns (coalesced reads of W)
 __global__ void __launch_bounds__(256)
-codebook_prep_kernel(const float *__restrict__ W, int K, int C, int C8, int nblkW, int Ntot,
-                     float *__restrict__ wimg, CodebookAux *__restrict__ aux)
+codebook_prep_kernel(const float *__restrict__ W, int K, int C, int nblkW, int Ntot,
+                     uint32_t off_bias, float *__restrict__ wimg, CodebookAux *__restrict__ aux)
 {
     const int lane = threadIdx.x & 31;
     const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
@@ -149,8 +152,7 @@ codebook_prep_kernel(const float *__restrict__ W, int K, int C, int C8, int nblk
             nrm2 += (double)w * (double)w;
             v = -2.0f * w;
         }
-        if (col < C8 || col >= C8 + 3)
-            *reinterpret_cast<float *>(base + img_offset(Ntot, row, col)) = v;
+        *reinterpret_cast<float *>(base + img_offset(Ntot, row, col)) = v;
     }
     for (int o = 16; o > 0; o >>= 1) nrm2 += __shfl_xor_sync(~0u, nrm2, o);
     bad = __any_sync(~0u, bad);
@@ -163,9 +165,13 @@ codebook_prep_kernel(const float *__restrict__ W, int K, int C, int C8, int nblk
         const float r1 = bias - h;
         const float m = __uint_as_float(__float_as_uint(r1) & 0xFFFFE000u);
         const float l = r1 - m;
-        *reinterpret_cast<float *>(base + img_offset(Ntot, row, C8 + 0)) = h;
-        *reinterpret_cast<float *>(base + img_offset(Ntot, row, C8 + 1)) = m;
-        *reinterpret_cast<float *>(base + img_offset(Ntot, row, C8 + 2)) = l;
+        float *b = reinterpret_cast<float *>(base + off_bias + bias_offset(row, 0));
+        b[0] = h;
+        b[1] = m;
+        b[2] = l;
+        b[3] = 0.f;
+        float *b2 = reinterpret_cast<float *>(base + off_bias + bias_offset(row, 4));
+        b2[0] = b2[1] = b2[2] = b2[3] = 0.f;
         if (row < K) {
             if (bad) atomicOr(&aux->nonfinite, 1);
             if (neg) atomicOr(&aux->w_has_negative, 1);
@@ -182,7 +188,7 @@ cudaError_t launch_codebook_prep(const float *W, int K, int C, const TcPlan &pla
 {
     const int rows_per_block = 8;
     codebook_prep_kernel<<<(plan.Ntot + rows_per_block - 1) / rows_per_block, 256, 0, stream>>>(
-        W, K, C, plan.C8, plan.nblkW, plan.Ntot, wimg, aux);
+        W, K, C, plan.nblkW, plan.Ntot, plan.off_bias, wimg, aux);
     count_launch();
     return cudaGetLastError();
 }

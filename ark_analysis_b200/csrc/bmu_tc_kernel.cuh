@@ -12,14 +12,24 @@ using namespace ptx;
 
 // Image layout (bytes): block b (32 columns) at b * Ntot * 128, row r at r * 128, 16-byte chunk c at
 // ((c ^ (r & 7)) << 4) -- exactly what TMA SWIZZLE_128B would have written, so one linear
-// cp.async.bulk brings it into place.  Column j < C of row k holds -2 * W[k, j]; columns
-// C8, C8+1, C8+2 hold ||w_k||^2 split into three tf32-exact terms (multiplied by the all-ones A
-// tile of the bias K-step); rows >= K hold zeros and a huge bias so they never win.
+// cp.async.bulk brings it into place.  Column j < C of row k holds -2 * W[k, j].  Behind the
+// blocks sits the bias block (plan.off_bias): one 8-column K-step per row in the no-swizzle
+// core-matrix layout (bias_offset), columns 0..2 = ||w_k||^2 split into three tf32-exact terms
+// (multiplied by the all-ones A tile of the bias K-step); rows >= K hold zeros and a huge bias so
+// they never win.
 __device__ __forceinline__ uint32_t img_offset(int Ntot, int row, int col)
 {
     const int b = col >> 5, cc = col & 31;
     return (uint32_t)b * (uint32_t)Ntot * 128u + (uint32_t)row * 128u +
            (uint32_t)((((cc >> 2) ^ (row & 7)) << 4) + ((cc & 3) << 2));
+}
+
+// K-major no-swizzle operand, 8 columns (one tf32 K-step) per row: 8-row x 16-byte core matrices,
+// the two K-adjacent ones 128 bytes apart (LBO), 8-row groups 256 bytes apart (SBO).
+__host__ __device__ __forceinline__ uint32_t bias_offset(int row, int col)
+{
+    return (uint32_t)(row >> 3) * 256u + (uint32_t)(col >> 2) * 128u + (uint32_t)(row & 7) * 16u +
+           (uint32_t)(col & 3) * 4u;
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -395,9 +405,10 @@ __device__ __noinline__ void step_update(const TcParams &p, int st, uint8_t *sme
                 const float r1 = bias - h;
                 const float m = __uint_as_float(__float_as_uint(r1) & 0xFFFFE000u);
                 const float l = r1 - m;
-                *reinterpret_cast<float *>(img + img_offset(pl.Ntot, k, pl.C8 + 0)) = h;
-                *reinterpret_cast<float *>(img + img_offset(pl.Ntot, k, pl.C8 + 1)) = m;
-                *reinterpret_cast<float *>(img + img_offset(pl.Ntot, k, pl.C8 + 2)) = l;
+                float *bb = reinterpret_cast<float *>(img + pl.off_bias + bias_offset(k, 0));
+                bb[0] = h;
+                bb[1] = m;
+                bb[2] = l;
                 float nr = (float)sqrt(tot) * 1.0000005f;
                 if (!(nr <= FLT_MAX)) nr = FLT_MAX;
                 atomicMax(&p.ctl->pp_wmax_bits[(st + 1) & 1], __float_as_int(nr));
@@ -670,8 +681,7 @@ bmu_tc_kernel(const __grid_constant__ CUtensorMap tmX, const TcParams p)
         {
             constexpr uint32_t idesc = umma_idesc_tf32(128, (uint32_t)NMMA);
             const uint64_t desc_ones = umma_desc_nosw(sbase + pl.off_ones, 128u, 256u);
-            // bias K-step: columns C8..C8+7 of the codebook image
-            const uint32_t bias_blk = (uint32_t)(pl.C8 >> 5), bias_off = (uint32_t)(pl.C8 & 31) * 4u;
+            // bias K-step: the no-swizzle block behind the image (8-row groups 256 bytes apart)
             const uint32_t wblk_bytes = (uint32_t)((NCH - 1) * NCHUNK + NMMA) * 128u;
             mbar_wait(bar_w, (uint32_t)st & 1u);
             uint32_t s = base_seq % (uint32_t)nstage;
@@ -696,8 +706,8 @@ bmu_tc_kernel(const __grid_constant__ CUtensorMap tmX, const TcParams p)
                         const uint64_t db = umma_desc_sw128(sbase + blk * wblk_bytes + wrow + ko);
                         mma_tf32(d_tmem, da, db, idesc, ks > 0 ? 1u : 0u);
                     }
-                    const uint64_t dbias =
-                        umma_desc_sw128(sbase + bias_blk * wblk_bytes + wrow + bias_off);
+                    const uint64_t dbias = umma_desc_nosw(
+                        sbase + pl.off_bias + (uint32_t)(c * NCHUNK / 8) * 256u, 128u, 256u);
                     mma_tf32(d_tmem, desc_ones, dbias, idesc, 1u);
                     mma_commit(bar_tfull + 8u * buf);
                     }

@@ -42,7 +42,7 @@ struct TcPlan {
     int C8;      // C rounded up to the tf32 MMA K-step (8)
     int ksteps;  // C8 / 8 data K-steps (+1 bias K-step)
     int nblkX;   // 32-channel (128-byte) blocks of one X tile  = ceil(C / 32)
-    int nblkW;   // 32-column blocks of the codebook image      = ceil((C8 + 8) / 32)
+    int nblkW;   // 32-column blocks of the codebook image      = ceil(C8 / 32)
     int SL;      // TMEM columns per epilogue slice            (template parameter)
     int spc;     // slices per accumulator chunk               (template parameter)
     int NCH;     // accumulator chunks per tile, 1 or 2        (template parameter)
@@ -54,6 +54,7 @@ struct TcPlan {
     int tmem_cols;
     int nstage;  // X tile pipeline depth (multiple of NG)
     uint32_t stage_bytes, wimg_bytes;
+    uint32_t off_bias;  // bias block inside the image: Ntot rows x 8 columns, no-swizzle core matrices
     uint32_t off_ones, off_x, off_bar, off_pairs;
     uint32_t off_acc, off_lab;  // fused accumulation (train mode): NG x K x (C+1) fp32 tables, then
                                 // NG x sort_stride bytes of per-group sort scratch (SortLayout)

@@ -47,7 +47,7 @@ def test_golden_vectors(name, flags):
 @pytest.mark.parametrize("kind", ["U", "P"])
 @pytest.mark.parametrize("C,K", [(16, 100), (32, 100), (40, 400), (100, 100), (64, 100),
                                  (15, 200), (8, 16), (33, 49), (22, 144), (4, 2), (1, 3),
-                                 (128, 100), (32, 512), (48, 256)])
+                                 (128, 100), (32, 512), (48, 256), (64, 400), (57, 300)])
 def test_tensor_core_kernel_bit_exact(kind, C, K):
     n = 128 * 150 + 77  # ragged last tile, more tiles than SMs so the pipelines wrap
     X = data(kind, n, C, seed=C * 1000 + K)
@@ -74,7 +74,7 @@ def test_trained_codebooks_bit_exact(C, K):
         assert int(stats[S._native.STAT_ROWS_FLAGGED]) > 0  # the recheck path was taken
 
 
-@pytest.mark.parametrize("C,K", [(16, 400), (32, 400), (24, 324), (40, 400)])
+@pytest.mark.parametrize("C,K", [(16, 400), (32, 400), (24, 324), (40, 400), (64, 400)])
 def test_two_chunk_variants_with_a_deep_pipeline(C, K):
     """K > 256 runs two accumulator chunks per tile whose TMEM buffers are shared by the two
     epilogue groups; with C <= 32 there is room for 6-8 X stages, and a warp that ran a tile ahead
