@@ -295,6 +295,35 @@ int pixie_columns_to_rows_f32(const double *cols, int64_t col_stride, int64_t n,
     return PIXIE_OK;
 }
 
+int pixie_label_histogram_i32(const int32_t *seg_labels, const int32_t *clusters, int64_t n,
+                              int32_t n_seg, int32_t n_clusters, int32_t *counts,
+                              unsigned long long *out_of_range_or_null, void *stream)
+{
+    if (n < 0 || n_seg < 1 || n_clusters < 1 || !counts || (n > 0 && (!seg_labels || !clusters)) ||
+        ((reinterpret_cast<uintptr_t>(seg_labels) | reinterpret_cast<uintptr_t>(clusters)) & 15u))
+        return PIXIE_ERR_INVALID_ARG;
+    PX_CUDA(launch_label_histogram(seg_labels, clusters, n, n_seg, n_clusters, counts,
+                                   out_of_range_or_null, num_sms_current_device(),
+                                   reinterpret_cast<cudaStream_t>(stream)));
+    return PIXIE_OK;
+}
+
+int pixie_scatter_labels_i16(const int32_t *row_index, const int32_t *column_index,
+                             const int32_t *clusters, int64_t n, const int16_t *id_map_or_null,
+                             int32_t map_len, int32_t H, int32_t W, int16_t *img,
+                             int32_t *winner_ws_or_null, unsigned long long *out_of_range_or_null,
+                             void *stream)
+{
+    if (n < 0 || n > INT32_MAX || H < 1 || W < 1 || !img || (n > 0 && (!row_index || !column_index || !clusters)) ||
+        (id_map_or_null && map_len < 1))
+        return PIXIE_ERR_INVALID_ARG;
+    PX_CUDA(launch_scatter_labels(row_index, column_index, clusters, n, id_map_or_null, map_len, H,
+                                  W, img, winner_ws_or_null, out_of_range_or_null,
+                                  num_sms_current_device(),
+                                  reinterpret_cast<cudaStream_t>(stream)));
+    return PIXIE_OK;
+}
+
 int pixie_som_online_f64(const float *X, int64_t n, int32_t C, int64_t ldX, double *W64,
                          int32_t xdim, int32_t ydim, const int64_t *sample_idx, int64_t niter,
                          double alpha0, double alpha1, double radius0, double radius1,

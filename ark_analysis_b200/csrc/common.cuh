@@ -154,6 +154,15 @@ cudaError_t launch_columns_to_rows(const double *cols, int64_t col_stride, int64
                                    const double *divisor, float *X, int64_t ldX, int num_sms,
                                    cudaStream_t stream);
 
+cudaError_t launch_label_histogram(const int32_t *seg, const int32_t *clu, int64_t n, int32_t n_seg,
+                                   int32_t n_clu, int32_t *counts, unsigned long long *bad,
+                                   int num_sms, cudaStream_t stream);
+cudaError_t launch_scatter_labels(const int32_t *row_index, const int32_t *col_index,
+                                  const int32_t *clu, int64_t n, const int16_t *id_map,
+                                  int32_t map_len, int32_t H, int32_t W, int16_t *img,
+                                  int32_t *winner, unsigned long long *bad, int num_sms,
+                                  cudaStream_t stream);
+
 size_t som_online_smem_bytes(int C, int K);
 cudaError_t launch_som_online(const float *X, int64_t n, int C, int64_t ldX, double *W, int xdim,
                               int ydim, const int64_t *sample_idx, int64_t niter,

@@ -222,6 +222,73 @@ def label_sums(X, labels, K):
     return SN
 
 
+
+def _as_i32(t, name, dev=None):
+    """Contiguous (hence 256-byte aligned) CUDA int32 copy / view of an integer tensor."""
+    if not isinstance(t, torch.Tensor):
+        t = torch.as_tensor(t)
+    if dev is None:
+        _require_cuda(t, name)
+        dev = t.device
+    t = t.to(device=dev)
+    if t.dtype != torch.int32:
+        t = t.to(torch.int32)
+    t = t.contiguous()
+    if t.data_ptr() % 16:
+        t = t.clone()
+    return t
+
+
+def label_histogram(seg_labels, clusters, n_seg, n_clusters, counts=None):
+    """N4: counts[s, c] = number of pixels with segmentation label s and cluster c -- the table
+    create_c2pc_data gets from groupby(['label', cluster]).size() + pivot (reference
+    cell_cluster_utils.py:119-132).  Both inputs are CUDA integer tensors of length n; pairs outside
+    [0, n_seg) x [0, n_clusters) (e.g. -1 for "no cluster") are skipped.  Returns (counts int32
+    [n_seg, n_clusters], number of skipped pixels); pass ``counts`` to accumulate over chunks."""
+    seg = _as_i32(seg_labels, "seg_labels")
+    dev = seg.device
+    clu = _as_i32(clusters, "clusters", dev)
+    if seg.dim() != 1 or clu.shape != seg.shape:
+        raise PixieError("seg_labels and clusters must be 1-D tensors of equal length")
+    if counts is None:
+        counts = torch.zeros((int(n_seg), int(n_clusters)), dtype=torch.int32, device=dev)
+    elif counts.dtype != torch.int32 or tuple(counts.shape) != (int(n_seg), int(n_clusters)) \
+            or not counts.is_contiguous() or counts.device != dev:
+        raise PixieError("counts must be a contiguous CUDA int32 [n_seg, n_clusters] tensor")
+    bad = torch.zeros(1, dtype=torch.int64, device=dev)
+    with torch.cuda.device(dev):
+        rc = _native.lib().pixie_label_histogram_i32(_ptr(seg), _ptr(clu), seg.numel(), int(n_seg),
+                                                     int(n_clusters), _ptr(counts), _ptr(bad),
+                                                     _stream(dev))
+    _native.check(rc, "pixie_label_histogram_i32")
+    return counts, bad
+
+
+def scatter_labels(row_index, column_index, clusters, H, W, id_map=None, unique=False):
+    """N4: the [H, W] int16 cluster mask with mask[row_index[i], column_index[i]] =
+    id_map[clusters[i]] (reference data_utils.py:523-551).  ``id_map`` is an int16 look-up table
+    indexed by cluster value (None = identity).  Duplicate coordinates resolve as numpy's fancy
+    assignment does (the last row wins) unless ``unique=True`` promises there are none."""
+    r = _as_i32(row_index, "row_index")
+    dev = r.device
+    c = _as_i32(column_index, "column_index", dev)
+    k = _as_i32(clusters, "clusters", dev)
+    if r.dim() != 1 or c.shape != r.shape or k.shape != r.shape:
+        raise PixieError("row_index, column_index and clusters must be 1-D tensors of equal length")
+    lut = None
+    if id_map is not None:
+        lut = torch.as_tensor(id_map).to(device=dev, dtype=torch.int16).contiguous()
+    img = torch.zeros((int(H), int(W)), dtype=torch.int16, device=dev)
+    winner = None if unique else torch.empty((int(H), int(W)), dtype=torch.int32, device=dev)
+    bad = torch.zeros(1, dtype=torch.int64, device=dev)
+    with torch.cuda.device(dev):
+        rc = _native.lib().pixie_scatter_labels_i16(
+            _ptr(r), _ptr(c), _ptr(k), r.numel(), _ptr(lut), 0 if lut is None else lut.numel(),
+            int(H), int(W), _ptr(img), _ptr(winner), _ptr(bad), _stream(dev))
+    _native.check(rc, "pixie_scatter_labels_i16")
+    return img, bad
+
+
 def som_accum(X, W32, tile_first, tile_stride, SN=None, flags=FLAG_AUTO, stats=None):
     """One mini-batch of the batch SOM: BMU of the rows of tiles tile_first, tile_first+stride, ...
     against W32 and their per-node sums/counts SN [K, C+1] float64."""

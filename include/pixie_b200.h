@@ -172,6 +172,33 @@ int pixie_som_train_peers_f32(const float *X, int64_t n, int32_t C, int64_t ldX,
                               void *workspace, size_t ws_bytes, uint32_t flags, void *stream);
 
 /*
+ * N4 -- consumers of the label array.
+ *
+ * pixie_label_histogram_i32: counts[s * n_clusters + c] += 1 for every pixel i with
+ * s = seg_labels[i], c = clusters[i]: the per-cell histogram of pixel cluster labels that
+ * create_c2pc_data builds with groupby(['label', cluster]).size() + pivot
+ * (/root/reference/src/ark/phenotyping/cell_cluster_utils.py:119-132).  `counts` is
+ * [n_seg x n_clusters] int32, ACCUMULATED into (zero it first; several FOV chunks may be added).
+ * Pixels whose pair lies outside [0, n_seg) x [0, n_clusters) are skipped and counted in
+ * *out_of_range_or_null.  seg_labels and clusters must be 16-byte aligned.
+ *
+ * pixie_scatter_labels_i16: img[row_index[i] * W + column_index[i]] = id_map[clusters[i]]
+ * (or (int16) clusters[i] when id_map is null): the cluster mask of generate_pixel_cluster_mask
+ * (/root/reference/src/ark/utils/data_utils.py:523-551; int16 "to allow for Photoshop loading").
+ * `img` is [H x W] int16, written in place (zero it first).  With `winner_ws` (an [H x W] int32
+ * scratch) duplicate coordinates resolve as numpy's fancy assignment does -- the LAST row wins --
+ * in two passes; with null, coordinates must be unique (as they are in a pixel table).
+ */
+int pixie_label_histogram_i32(const int32_t *seg_labels, const int32_t *clusters, int64_t n,
+                              int32_t n_seg, int32_t n_clusters, int32_t *counts,
+                              unsigned long long *out_of_range_or_null, void *stream);
+int pixie_scatter_labels_i16(const int32_t *row_index, const int32_t *column_index,
+                             const int32_t *clusters, int64_t n, const int16_t *id_map_or_null,
+                             int32_t map_len, int32_t H, int32_t W, int16_t *img,
+                             int32_t *winner_ws_or_null, unsigned long long *out_of_range_or_null,
+                             void *stream);
+
+/*
  * Host-buffer entry point with pyFlowSOM.map_data_to_nodes' shape (what a ctypes/cgo/JNI binding
  * of the reference would call): nodes [K x C] and data [n x C] in HOST memory (fp32, row-major,
  * contiguous), labels int32[n] and optional dists double[n] in host memory.  Streams the rows
