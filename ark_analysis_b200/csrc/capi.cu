@@ -295,6 +295,65 @@ int pixie_columns_to_rows_f32(const double *cols, int64_t col_stride, int64_t n,
     return PIXIE_OK;
 }
 
+namespace {
+struct PreWs {
+    double *tmp, *rowsum;
+    int32_t *flags, *pos;
+    void *scan;
+    size_t scan_bytes, total;
+};
+PreWs carve_pre(void *base, int64_t n, int C)
+{
+    PreWs w{};
+    size_t off = 0;
+    auto take = [&](size_t bytes) {
+        void *p = (char *)base + off;
+        off += align_up(bytes, 256);
+        return p;
+    };
+    w.tmp = (double *)take(sizeof(double) * (size_t)n * C);
+    w.rowsum = (double *)take(sizeof(double) * (size_t)n);
+    w.flags = (int32_t *)take(sizeof(int32_t) * (size_t)n);
+    w.pos = (int32_t *)take(sizeof(int32_t) * (size_t)n);
+    w.scan_bytes = pixie::preprocess_scan_bytes(n);
+    w.scan = take(w.scan_bytes);
+    w.total = off;
+    return w;
+}
+}  // namespace
+
+size_t pixie_preprocess_workspace_bytes(int32_t H, int32_t W, int32_t C)
+{
+    if (H < 1 || W < 1 || C < 1) return 0;
+    return carve_pre(nullptr, (int64_t)H * W, C).total;
+}
+
+int pixie_preprocess_fov_f64(const void *img, int32_t H, int32_t W, int32_t C,
+                             const double *norm_vect_or_null, const double *taps_host,
+                             int32_t radius, double pixel_thresh_val,
+                             const int32_t *seg_labels_or_null, double *blurred, double *X64_or_null,
+                             float *X32_or_null, int64_t ldX32, int32_t *row_index,
+                             int32_t *column_index, int32_t *labels_out_or_null, int64_t *n_kept,
+                             void *workspace, size_t ws_bytes, uint32_t flags, void *stream)
+{
+    if (H < 1 || W < 1 || C < 1 || (int64_t)H * W >= ((int64_t)1 << 31) || !img || !blurred ||
+        radius < 0 || radius > pixie::kMaxBlurRadius || (radius > 0 && !taps_host))
+        return PIXIE_ERR_INVALID_ARG;
+    const int blur_only = (flags & PIXIE_PREPROCESS_BLUR_ONLY) ? 1 : 0;
+    if (!blur_only && (!row_index || !column_index || !n_kept || (X32_or_null && ldX32 < C)))
+        return PIXIE_ERR_INVALID_ARG;
+    PreWs ws = carve_pre(workspace, (int64_t)H * W, C);
+    if (!workspace || ws_bytes < ws.total) return PIXIE_ERR_WORKSPACE;
+    PX_CUDA(pixie::launch_preprocess(img, (flags & PIXIE_PREPROCESS_IMG_F64) ? 1 : 0, H, W, C, norm_vect_or_null, taps_host, radius,
+                                     pixel_thresh_val, seg_labels_or_null, blurred, ws.tmp,
+                                     ws.rowsum, ws.flags, ws.pos, ws.scan, ws.scan_bytes,
+                                     X64_or_null, X32_or_null, ldX32, row_index, column_index,
+                                     labels_out_or_null, n_kept, blur_only,
+                                     num_sms_current_device(),
+                                     reinterpret_cast<cudaStream_t>(stream)));
+    return PIXIE_OK;
+}
+
 int pixie_label_histogram_i32(const int32_t *seg_labels, const int32_t *clusters, int64_t n,
                               int32_t n_seg, int32_t n_clusters, int32_t *counts,
                               unsigned long long *out_of_range_or_null, void *stream)

@@ -163,6 +163,16 @@ cudaError_t launch_scatter_labels(const int32_t *row_index, const int32_t *col_i
                                   int32_t *winner, unsigned long long *bad, int num_sms,
                                   cudaStream_t stream);
 
+constexpr int kMaxBlurRadius = 32;  // gaussian taps either side (scipy: int(4 * sigma + 0.5))
+size_t preprocess_scan_bytes(int64_t n);
+cudaError_t launch_preprocess(const void *img, int img_is_f64, int H, int W, int C, const double *norm,
+                              const double *taps_host, int radius, double thresh,
+                              const int32_t *seg, double *blurred, double *tmp, double *rowsum,
+                              int32_t *flags, int32_t *pos, void *scan_tmp, size_t scan_bytes,
+                              double *X64, float *X32, int64_t ldX32, int32_t *row_index,
+                              int32_t *col_index, int32_t *labels_out, int64_t *n_kept,
+                              int stop_after_blur, int num_sms, cudaStream_t stream);
+
 size_t som_online_smem_bytes(int C, int K);
 cudaError_t launch_som_online(const float *X, int64_t n, int C, int64_t ldX, double *W, int xdim,
                               int ydim, const int64_t *sample_idx, int64_t niter,

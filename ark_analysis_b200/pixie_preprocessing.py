@@ -1,0 +1,125 @@
+"""Pixie pixel preprocessing with the arithmetic on the GPU.
+
+Mirrors ``create_fov_pixel_data`` of the reference (src/ark/phenotyping/pixie_preprocessing.py:18-80)
+-- same arguments, same two DataFrames -- and adds the device-native form the SOM path wants:
+``preprocess_fov_device`` leaves the normalised pixel matrix in HBM (fp32 rows for
+``som.bmu`` / ``som.train_som``, fp64 rows for the Feather file), so a FOV goes image -> labels without
+a DataFrame in between.  Blur, filter and row normalisation run in ``pixie_preprocess_fov_f64``
+(csrc/preprocess_kernels.cu) in fp64 and in the reference's operation order: bit-identical values.
+"""
+import ctypes
+import re
+
+import numpy as np
+import torch
+
+from . import _native
+from ._native import PixieError
+from . import som as _som
+
+BLUR_ONLY, IMG_F64 = 1, 2
+MAX_RADIUS = 32
+
+
+def gaussian_taps(sigma, truncate=4.0):
+    """Half of scipy.ndimage's 1-D gaussian kernel, centre first (``_gaussian_kernel1d`` with
+    order 0: exp(-0.5 / sigma^2 * x^2) normalised by the sum over [-radius, radius])."""
+    sd = float(sigma)
+    radius = int(truncate * sd + 0.5)
+    if sd <= 1e-15 or radius == 0:
+        return np.ones(1, np.float64), 0   # scipy skips axes with sigma <= 1e-15
+    if radius > MAX_RADIUS:
+        raise PixieError(f"blur radius {radius} exceeds the kernel's limit of {MAX_RADIUS} taps")
+    x = np.arange(-radius, radius + 1)
+    phi = np.exp(-0.5 / (sd * sd) * x ** 2)
+    phi = phi / phi.sum()
+    return np.ascontiguousarray(phi[radius:]), radius
+
+
+def natural_key(name):
+    """Sort key of ``natsort.natsort_key`` for plain channel names: digit runs compare as numbers."""
+    return [int(t) if t.isdigit() else t for t in re.split(r'(\d+)', str(name))]
+
+
+def preprocess_fov_device(img, norm_vect=None, pixel_thresh_val=0.0, blur_factor=2,
+                          seg_labels=None, want_x64=True, want_x32=True, blur_only=False,
+                          device=None):
+    """Run the preprocessing of one FOV on the GPU.
+
+    ``img``: [H, W, C] image stack, float32 (divided by ``norm_vect`` in fp64, as preprocess_fov
+    does) or float64 (already normalised, what create_fov_pixel_data receives); numpy or CUDA.
+    Returns a dict of CUDA tensors: ``blurred`` [H, W, C] fp64, and unless ``blur_only``:
+    ``X64`` [n, C] fp64, ``X32`` [n, C] fp32 (row pitch a multiple of 4 floats: feeds som.bmu
+    directly), ``row_index`` / ``column_index`` / ``label`` int32 [n], ``n`` (int)."""
+    dev = torch.device(device) if device is not None else _som._default_device()
+    t = torch.as_tensor(img)
+    if t.dim() != 3:
+        raise PixieError("img must be [H, W, C]")
+    if t.dtype not in (torch.float32, torch.float64):
+        t = t.to(torch.float32)
+    t = t.to(dev).contiguous()
+    H, W, C = (int(v) for v in t.shape)
+    flags = (IMG_F64 if t.dtype == torch.float64 else 0) | (BLUR_ONLY if blur_only else 0)
+    taps, radius = gaussian_taps(blur_factor)
+    norm = None
+    if norm_vect is not None:
+        norm = torch.as_tensor(np.asarray(norm_vect, np.float64).reshape(-1)).to(dev)
+        if norm.numel() != C:
+            raise PixieError("norm_vect must hold one value per channel")
+    seg = None
+    if seg_labels is not None and not blur_only:
+        seg = torch.as_tensor(np.ascontiguousarray(seg_labels)).reshape(-1).to(dev).to(torch.int32)
+        if seg.numel() != H * W:
+            raise PixieError("seg_labels must have H * W elements")
+    n = H * W
+    lib = _native.lib()
+    ws = torch.empty(lib.pixie_preprocess_workspace_bytes(H, W, C), dtype=torch.uint8, device=dev)
+    out = {"blurred": torch.empty((H, W, C), dtype=torch.float64, device=dev)}
+    X64 = X32 = rows = cols = labs = nk = None
+    ld = (C + 3) // 4 * 4
+    if not blur_only:
+        X64 = torch.empty((n, C), dtype=torch.float64, device=dev) if want_x64 else None
+        X32 = (torch.zeros if ld != C else torch.empty)((n, ld), dtype=torch.float32, device=dev) \
+            if want_x32 else None
+        rows = torch.empty(n, dtype=torch.int32, device=dev)
+        cols = torch.empty(n, dtype=torch.int32, device=dev)
+        labs = torch.empty(n, dtype=torch.int32, device=dev) if seg is not None else None
+        nk = torch.zeros(1, dtype=torch.int64, device=dev)
+    p = _som._ptr
+    with torch.cuda.device(dev):
+        rc = lib.pixie_preprocess_fov_f64(
+            p(t), H, W, C, p(norm), taps.ctypes.data_as(ctypes.c_void_p), radius,
+            float(pixel_thresh_val), p(seg), p(out["blurred"]), p(X64), p(X32), ld, p(rows),
+            p(cols), p(labs), p(nk), p(ws), ws.numel(), flags, _som._stream(dev))
+    _native.check(rc, "pixie_preprocess_fov_f64")
+    if blur_only:
+        return out
+    k = int(nk.item())   # also orders the host's view after the kernels
+    out.update(n=k, X64=None if X64 is None else X64[:k],
+               X32=None if X32 is None else X32[:k, :C],
+               row_index=rows[:k], column_index=cols[:k],
+               label=None if labs is None else labs[:k])
+    return out
+
+
+def create_fov_pixel_data(fov, channels, img_data, seg_labels, pixel_thresh_val,
+                          blur_factor=2, subset_proportion=0.1):
+    """The reference's ``create_fov_pixel_data``: (pixel_mat, pixel_mat_subset) for one FOV --
+    blurred, thresholded, row-normalised channel columns plus ``fov``, ``row_index``,
+    ``column_index`` (and ``label`` when ``seg_labels`` is given); the subset is
+    ``pixel_mat.sample(frac=subset_proportion)`` under numpy's global seed, as there.  Like the
+    reference, ``channels`` is sorted in place and ``img_data`` receives the blurred planes."""
+    import pandas as pd
+    channels.sort(key=natural_key)
+    res = preprocess_fov_device(img_data, None, pixel_thresh_val, blur_factor, seg_labels,
+                                want_x64=True, want_x32=False)
+    if isinstance(img_data, np.ndarray) and img_data.dtype == np.float64 and img_data.flags.writeable:
+        img_data[...] = res["blurred"].cpu().numpy()
+    pixel_mat = pd.DataFrame(res["X64"].cpu().numpy(), columns=channels)
+    pixel_mat['fov'] = fov
+    pixel_mat['row_index'] = res["row_index"].cpu().numpy().astype(np.int64)
+    pixel_mat['column_index'] = res["column_index"].cpu().numpy().astype(np.int64)
+    if seg_labels is not None:
+        pixel_mat['label'] = res["label"].cpu().numpy().astype(np.asarray(seg_labels).dtype)
+    pixel_mat_subset = pixel_mat.sample(frac=subset_proportion)
+    return pixel_mat, pixel_mat_subset

@@ -172,6 +172,36 @@ int pixie_som_train_peers_f32(const float *X, int64_t n, int32_t C, int64_t ldX,
                               void *workspace, size_t ws_bytes, uint32_t flags, void *stream);
 
 /*
+ * N3 -- pixel preprocessing on the device: the arithmetic of
+ * create_fov_pixel_data / preprocess_fov (/root/reference/src/ark/phenotyping/
+ * pixie_preprocessing.py:18-80, :154-161) and normalize_rows (pixel_cluster_utils.py:109-142).
+ *
+ * img [H x W x C] fp32 (fp64 with PIXIE_PREPROCESS_IMG_F64; channel fastest, device) -> x = float64(img) / norm_vect[c]
+ * -> per-channel 2-D gaussian filter (scipy.ndimage.gaussian_filter: separable, axis 0 then axis 1,
+ * mode 'reflect'; `taps_host` is a HOST array of radius + 1 fp64 weights, taps_host[j] = weight at
+ * distance j, computed by the caller exactly as scipy's _gaussian_kernel1d does; radius 0 = no
+ * blur) -> `blurred` [H x W x C] fp64 (device, caller-owned)
+ * -> keep pixels with sum_c x > pixel_thresh_val and any x != 0
+ * -> kept pixels in image order, each divided by its channel sum:
+ *      X64 [n_kept x C] fp64 and/or X32 [n_kept x C] fp32 at row pitch ldX32 (capacity H*W rows),
+ *      row_index / column_index int32 [H*W], labels_out (seg_labels of the kept pixels) and the
+ *      device scalar *n_kept.
+ * fp64 throughout, in the reference's operation order: `blurred`, the kept set and X64 are
+ * bit-identical to the scipy + pandas route.  PIXIE_PREPROCESS_BLUR_ONLY stops after the blur.
+ * Asynchronous on `stream`; workspace of pixie_preprocess_workspace_bytes(H, W, C) bytes.
+ */
+#define PIXIE_PREPROCESS_BLUR_ONLY 1u
+#define PIXIE_PREPROCESS_IMG_F64 2u /* img holds fp64 values (already normalised images) */
+size_t pixie_preprocess_workspace_bytes(int32_t H, int32_t W, int32_t C);
+int pixie_preprocess_fov_f64(const void *img, int32_t H, int32_t W, int32_t C,
+                             const double *norm_vect_or_null, const double *taps_host,
+                             int32_t radius, double pixel_thresh_val,
+                             const int32_t *seg_labels_or_null, double *blurred, double *X64_or_null,
+                             float *X32_or_null, int64_t ldX32, int32_t *row_index,
+                             int32_t *column_index, int32_t *labels_out_or_null, int64_t *n_kept,
+                             void *workspace, size_t ws_bytes, uint32_t flags, void *stream);
+
+/*
  * N4 -- consumers of the label array.
  *
  * pixie_label_histogram_i32: counts[s * n_clusters + c] += 1 for every pixel i with

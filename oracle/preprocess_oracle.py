@@ -1,0 +1,100 @@
+"""CPU oracle for the pixel preprocessing row -- TEST INFRASTRUCTURE ONLY.
+
+Two independent statements of /root/reference/src/ark/phenotyping/pixie_preprocessing.py:18-80
+(+ normalize_rows, pixel_cluster_utils.py:109-142):
+
+* ``create_fov_pixel_data``: the reference's own route -- ``scipy.ndimage.gaussian_filter`` per
+  channel and the pandas filter / normalise / sample calls.  scipy and pandas ARE the reference's
+  dependencies for this path and are installed, so this half is the reference's arithmetic itself:
+  PINNED.  (alpineer / natsort are absent: the natural channel sort is restated.)
+* ``preprocess_explicit``: numpy with every operation spelled out in the order the CUDA kernels
+  use (scipy's symmetric correlate1d order, sequential channel sums, IEEE division).
+  tests/test_preprocess_oracle.py checks the two agree BIT FOR BIT and against committed golden
+  vectors (tests/golden/preprocess_*.npz, made by tests/golden/make_golden.py with scipy 1.18 /
+  pandas 3.0)."""
+import re
+
+import numpy as np
+import pandas as pd
+from scipy import ndimage
+
+
+def _natural_key(name):
+    return [int(t) if t.isdigit() else t for t in re.split(r'(\d+)', str(name))]
+
+
+def create_fov_pixel_data(fov, channels, img_data, seg_labels, pixel_thresh_val,
+                          blur_factor=2, subset_proportion=0.1):
+    """pixie_preprocessing.py:45-80 with scipy + pandas."""
+    channels.sort(key=_natural_key)
+    for m in range(len(channels)):
+        img_data[:, :, m] = ndimage.gaussian_filter(img_data[:, :, m], sigma=blur_factor)
+    mat = pd.DataFrame(img_data.reshape(-1, len(channels)), columns=channels)
+    mat['fov'] = fov
+    mat['row_index'] = np.repeat(range(img_data.shape[0]), img_data.shape[1])
+    mat['column_index'] = np.tile(range(img_data.shape[1]), img_data.shape[0])
+    if seg_labels is not None:
+        mat['label'] = seg_labels.flatten()
+    rowsums = mat[channels].sum(axis=1)
+    mat = mat.loc[rowsums > pixel_thresh_val, :].reset_index(drop=True)
+    mat = mat.loc[(mat[channels] != 0).any(axis=1), :].reset_index(drop=True)
+    # normalize_rows (pixel_cluster_utils.py:109-142)
+    sub = mat[channels]
+    sub = sub.div(sub.sum(axis=1), axis=0)
+    meta = ['fov', 'row_index', 'column_index'] + (['label'] if seg_labels is not None else [])
+    sub[meta] = mat.loc[sub.index.values, meta]
+    return sub, sub.sample(frac=subset_proportion)
+
+
+def gaussian_taps(sigma, truncate=4.0):
+    radius = int(truncate * float(sigma) + 0.5)
+    x = np.arange(-radius, radius + 1)
+    phi = np.exp(-0.5 / (float(sigma) ** 2) * x ** 2)
+    phi = phi / phi.sum()
+    return phi[radius:], radius
+
+
+def _correlate_axis(a, axis, taps, radius):
+    """scipy NI_Correlate1D, symmetric branch, mode 'reflect': centre product first, then the tap
+    pairs from the farthest to the nearest, each (left + right) * w added to the running sum."""
+    a = np.moveaxis(a, axis, 0)
+    n = a.shape[0]
+    idx = np.arange(-radius, n + radius)
+    if n == 1:
+        idx[:] = 0
+    else:
+        while ((idx < 0) | (idx >= n)).any():
+            idx = np.where(idx < 0, -idx - 1, idx)
+            idx = np.where(idx >= n, 2 * n - 1 - idx, idx)
+    p = a[idx]
+    acc = p[radius:radius + n] * taps[0]
+    for j in range(radius, 0, -1):
+        acc = acc + (p[radius - j:radius - j + n] + p[radius + j:radius + j + n]) * taps[j]
+    return np.moveaxis(acc, 0, axis)
+
+
+def gaussian_blur_explicit(x, sigma):
+    """[H, W, C] fp64 -> per-channel 2-D blur, axis 0 then axis 1."""
+    taps, radius = gaussian_taps(sigma)
+    if radius == 0:
+        return x.copy()
+    return _correlate_axis(_correlate_axis(x, 0, taps, radius), 1, taps, radius)
+
+
+def preprocess_explicit(img, norm_vect, pixel_thresh_val, blur_factor, seg_labels=None):
+    """img fp32/fp64 [H, W, C] -> dict(blurred, X64, X32, row_index, column_index, label)."""
+    x = np.asarray(img).astype(np.float64)
+    if norm_vect is not None:
+        x = x / np.asarray(norm_vect, np.float64).reshape(1, 1, -1)
+    b = gaussian_blur_explicit(x, blur_factor)
+    H, W, C = b.shape
+    flat = b.reshape(-1, C)
+    s = np.zeros(H * W)
+    for c in range(C):
+        s = s + flat[:, c]
+    keep = (s > pixel_thresh_val) & (flat != 0).any(axis=1)
+    ii = np.flatnonzero(keep)
+    X64 = flat[ii] / s[ii, None]
+    return {"blurred": b, "X64": X64, "X32": X64.astype(np.float32),
+            "row_index": (ii // W).astype(np.int32), "column_index": (ii % W).astype(np.int32),
+            "label": None if seg_labels is None else np.asarray(seg_labels).reshape(-1)[ii]}

@@ -1,0 +1,101 @@
+"""GPU parity tests of the N3 row: pixie_preprocess_fov_f64 through the C ABI
+and the create_fov_pixel_data mirror, against the reference's scipy + pandas route (golden vectors
+and live, oracle/preprocess_oracle.py).  fp64 in the reference's operation order: BIT-EXACT."""
+import os
+
+import numpy as np
+import pandas as pd
+import pytest
+import torch
+from scipy import ndimage
+
+from oracle import preprocess_oracle as PO
+from ark_analysis_b200 import pixie_preprocessing as PP, som as S
+
+pytestmark = pytest.mark.gpu
+GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+CASES = ["preprocess_41x37x5.npz", "preprocess_6x50x3_sparse.npz", "preprocess_48x40x8.npz"]
+
+
+@pytest.mark.parametrize("name", CASES)
+def test_golden_reference_outputs(name):
+    g = np.load(os.path.join(GOLD, name))
+    out = PP.preprocess_fov_device(g["img"], g["norm"], float(g["thresh"]), float(g["sigma"]), g["seg"])
+    np.testing.assert_array_equal(out["blurred"].cpu().numpy(), g["blurred"])
+    assert out["n"] == len(g["X64"])
+    np.testing.assert_array_equal(out["X64"].cpu().numpy(), g["X64"])
+    np.testing.assert_array_equal(out["X32"].cpu().numpy(), g["X64"].astype(np.float32))
+    np.testing.assert_array_equal(out["row_index"].cpu().numpy(), g["row_index"])
+    np.testing.assert_array_equal(out["column_index"].cpu().numpy(), g["column_index"])
+    np.testing.assert_array_equal(out["label"].cpu().numpy(), g["label"])
+
+
+@pytest.mark.parametrize("shape,sigma", [((33, 29, 4), 2), ((5, 70, 2), 2), ((70, 3, 2), 2),
+                                         ((40, 40, 3), 1), ((20, 20, 2), 3.5), ((1, 9, 1), 2),
+                                         ((16, 16, 1), 0)])
+def test_blur_matches_scipy_bit_for_bit(shape, sigma, rng):
+    x = rng.random(shape) * 10
+    ref = np.stack([ndimage.gaussian_filter(x[:, :, c], sigma=sigma) for c in range(shape[2])], -1)
+    out = PP.preprocess_fov_device(x, blur_factor=sigma, blur_only=True)      # fp64 input path
+    np.testing.assert_array_equal(out["blurred"].cpu().numpy(), ref)
+
+
+def test_everything_filtered_and_nothing_filtered(rng):
+    img = rng.random((20, 24, 3)).astype(np.float32)
+    none = PP.preprocess_fov_device(img, None, 1e9, 2)
+    assert none["n"] == 0 and none["X64"].shape == (0, 3)
+    every = PP.preprocess_fov_device(img, None, -1.0, 2)
+    assert every["n"] == 20 * 24
+    zeros = PP.preprocess_fov_device(np.zeros((20, 24, 3), np.float32), None, -1.0, 2)
+    assert zeros["n"] == 0      # rows whose channels are all zero go even when the sum passes
+
+
+def test_create_fov_pixel_data_mirror_equals_the_pandas_route(rng):
+    H, W, C = 48, 52, 7
+    img = rng.gamma(0.5, 1.0, (H, W, C)).astype(np.float32)
+    norm = rng.uniform(0.5, 2.0, C)
+    seg = rng.integers(0, 9, (H, W))
+    for seg_arg in (seg, None):
+        ch_a = ['chan10', 'chan2', 'chan1', 'CD45', 'CD4', 'HH3', 'Ki67']
+        ch_b = list(ch_a)
+        xa = img / norm.reshape(1, 1, C)
+        xb = xa.copy()
+        np.random.seed(7)
+        ref_mat, ref_sub = PO.create_fov_pixel_data('fov3', ch_a, xa, seg_arg, 2.8)
+        np.random.seed(7)
+        mat, sub = PP.create_fov_pixel_data('fov3', ch_b, xb, seg_arg, 2.8)
+        assert ch_a == ch_b                           # sorted in place, naturally
+        np.testing.assert_array_equal(xa, xb)         # img_data receives the blurred planes
+        pd.testing.assert_frame_equal(mat, ref_mat)
+        pd.testing.assert_frame_equal(sub, ref_sub)   # same rows sampled under the same seed
+        assert 0 < len(mat) < H * W
+
+
+def test_full_fov_size_properties_and_device_handoff():
+    """cfg2-sized FOV (1024 x 1024 x 32): two channels of the blur against scipy bit for bit, rows
+    sum to one, indices in image order, and the fp32 matrix feeds the BMU kernel as it is."""
+    H = W = 1024
+    C = 32
+    g = torch.Generator(device="cuda").manual_seed(3)
+    img = torch.empty((H, W, C), device="cuda").exponential_(1.0, generator=g)
+    img *= (torch.rand((H, W, 1), device="cuda", generator=g) > 0.3)
+    norm = np.linspace(0.5, 2.0, C)
+    out = PP.preprocess_fov_device(img, norm, 20.0, 2)
+    host = img.cpu().numpy()
+    for c in (0, 17):
+        ref = ndimage.gaussian_filter(host[:, :, c].astype(np.float64) / norm[c], sigma=2)
+        np.testing.assert_array_equal(out["blurred"][:, :, c].cpu().numpy(), ref)
+    n = out["n"]
+    assert 0 < n < H * W
+    sums = out["X64"].sum(1)
+    assert float((sums - 1).abs().max()) < 1e-13
+    lin = out["row_index"].long() * W + out["column_index"].long()
+    assert bool((lin[1:] > lin[:-1]).all())
+    b = out["blurred"].reshape(-1, C)
+    keep = (b.sum(1) > 20.0)
+    assert abs(int(keep.sum()) - n) <= 2          # torch's sum order may flip a boundary pixel
+    # hand-off: the fp32 rows go straight into the assignment kernel
+    W0 = out["X32"][:100].contiguous()
+    lab = S.bmu(out["X32"], W0)
+    torch.cuda.synchronize()
+    assert lab.shape == (n,) and int(lab.min()) >= 1 and int(lab.max()) <= 100

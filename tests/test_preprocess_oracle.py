@@ -1,0 +1,57 @@
+"""CPU tests of the N3 oracle: the explicit-order numpy restatement against the reference's own
+scipy + pandas route, bit for bit, on seeded cases and on the committed golden vectors."""
+import os
+
+import numpy as np
+import pytest
+from scipy import ndimage
+
+from oracle import preprocess_oracle as PO
+
+GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+CASES = ["preprocess_41x37x5.npz", "preprocess_6x50x3_sparse.npz", "preprocess_48x40x8.npz"]
+
+
+@pytest.mark.parametrize("name", CASES)
+def test_explicit_restatement_reproduces_the_golden_reference_outputs(name):
+    g = np.load(os.path.join(GOLD, name))
+    out = PO.preprocess_explicit(g["img"], g["norm"], float(g["thresh"]), float(g["sigma"]), g["seg"])
+    np.testing.assert_array_equal(out["blurred"], g["blurred"])
+    np.testing.assert_array_equal(out["X64"], g["X64"])
+    np.testing.assert_array_equal(out["row_index"], g["row_index"])
+    np.testing.assert_array_equal(out["column_index"], g["column_index"])
+    np.testing.assert_array_equal(out["label"], g["label"])
+    assert 0 < len(out["X64"]) < g["img"].shape[0] * g["img"].shape[1]   # the filter did filter
+
+
+@pytest.mark.parametrize("shape,sigma", [((33, 29, 4), 2), ((5, 70, 2), 2), ((70, 3, 2), 2),
+                                         ((40, 40, 3), 1), ((20, 20, 2), 3.5), ((1, 9, 1), 2)])
+def test_blur_order_matches_scipy_bit_for_bit(shape, sigma, rng):
+    x = rng.random(shape) * 10
+    ref = np.stack([ndimage.gaussian_filter(x[:, :, c], sigma=sigma) for c in range(shape[2])], -1)
+    np.testing.assert_array_equal(PO.gaussian_blur_explicit(x, sigma), ref)
+
+
+def test_pandas_route_against_explicit_on_a_fresh_case(rng):
+    H, W, C = 48, 52, 7
+    img = rng.gamma(0.5, 1.0, (H, W, C)).astype(np.float32)
+    norm = rng.uniform(0.5, 2.0, C)
+    seg = rng.integers(0, 9, (H, W))
+    channels = ['c%d' % i for i in range(C)]
+    x = img / norm.reshape(1, 1, C)
+    np.random.seed(42)
+    mat, sub = PO.create_fov_pixel_data('f', channels, x, seg, 2.0)
+    out = PO.preprocess_explicit(img, norm, 2.0, 2, seg)
+    np.testing.assert_array_equal(mat[channels].values, out["X64"])
+    np.testing.assert_array_equal(mat['row_index'].values, out["row_index"])
+    np.testing.assert_array_equal(mat['label'].values, out["label"])
+    assert list(mat.columns) == channels + ['fov', 'row_index', 'column_index', 'label']
+    assert len(sub) == round(0.1 * len(mat))
+    # rows sum to 1 (pixie_preprocessing_test.py:79 of the reference asserts the same)
+    np.testing.assert_allclose(mat[channels].sum(axis=1).values, 1.0, rtol=0, atol=1e-12)
+
+
+def test_channel_names_sort_naturally():
+    names = ['chan10', 'chan2', 'chan1', 'CD45', 'CD4']
+    names.sort(key=PO._natural_key)
+    assert names == ['CD4', 'CD45', 'chan1', 'chan2', 'chan10']
