@@ -17,8 +17,11 @@ peak = bench.measured_peaks()[0]
 free = torch.cuda.mem_get_info()[0]
 rows = ["| N | C | K | kernel | ms | Gpx/s | GB/s | frac of %.0f GB/s | rows rechecked | note |" % peak,
         "|---|---|---|---|---|---|---|---|---|---|"]
-for C in (16, 32, 64):
-    for K in (100, 400):
+import os  # noqa: E402
+only_c = [int(v) for v in os.environ.get("SWEEP_C", "16,32,64").split(",")]
+only_k = [int(v) for v in os.environ.get("SWEEP_K", "100,400").split(",")]
+for C in only_c:
+    for K in only_k:
         for N in (10**6, 10**7, 10**8, 10**9):
             if N > max_n:
                 continue
