@@ -202,7 +202,7 @@ def run_reference(args):
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line), flush=True)
+    _emit(line)
 
 
 # ------------------------------------------------------------------------------------------------
@@ -398,12 +398,27 @@ def run_gpu(args):
             "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches),
             "clocks": clocks,
         }
-        print(json.dumps(line), flush=True)
+        _emit(line)
     if distributed:
         dist.destroy_process_group()
 
 
+_JSON_OUT = None
+
+
+def _emit(line):
+    """The ONE JSON line goes to the real stdout; everything else libraries print to fd 1 during the
+    run (NCCL's "NCCL version ..." banner when NCCL_DEBUG is set on the box) was diverted to
+    stderr by main()."""
+    out = _JSON_OUT if _JSON_OUT is not None else sys.stdout
+    print(json.dumps(line), file=out, flush=True)
+
+
 def main():
+    global _JSON_OUT
+    sys.stdout.flush()
+    _JSON_OUT = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=20)
