@@ -238,6 +238,42 @@ def test_product_path_fails_loudly_without_a_gpu():
         som.map_data_to_nodes(X[:4], X)
     with pytest.raises(som.PixieError):
         som.bmu(torch.zeros(4, 4), torch.zeros(2, 4))
+    # the rows either side of the SOM (N3 / N4) have no CPU route either
+    from ark_analysis_b200 import pixie_preprocessing as PP
+    z = torch.zeros(4, dtype=torch.int32)
+    with pytest.raises(som.PixieError):
+        som.label_histogram(z, z, 2, 2)
+    with pytest.raises(som.PixieError):
+        som.scatter_labels(z, z, z, 2, 2)
+    with pytest.raises(som.PixieError):
+        PP.preprocess_fov_device(np.zeros((4, 4, 2), np.float32))
+
+
+def test_gaussian_taps_are_scipys_kernel_bit_for_bit():
+    """The blur weights are computed on the host and handed to the kernel: they must be the very
+    numbers scipy.ndimage uses (its private _gaussian_kernel1d when importable, else the public
+    filter's impulse response)."""
+    from scipy import ndimage
+    from ark_analysis_b200 import pixie_preprocessing as PP
+    for sigma in (1, 2, 2.5, 3.5):
+        taps, radius = PP.gaussian_taps(sigma)
+        assert radius == int(4.0 * sigma + 0.5) and taps.shape == (radius + 1,)
+        try:
+            from scipy.ndimage._filters import _gaussian_kernel1d
+            ref = _gaussian_kernel1d(float(sigma), 0, radius)[::-1]
+            np.testing.assert_array_equal(taps, ref[radius:])
+        except ImportError:
+            pass
+        impulse = np.zeros(4 * radius + 1)
+        impulse[2 * radius] = 1.0
+        resp = ndimage.gaussian_filter1d(impulse, sigma)
+        np.testing.assert_array_equal(resp[2 * radius:3 * radius + 1], taps)
+    assert PP.gaussian_taps(0)[1] == 0
+    with pytest.raises(som.PixieError):
+        PP.gaussian_taps(20)      # radius 80 > the kernel's 32 taps
+    names = ['chan10', 'chan2', 'chan1', 'CD45', 'CD4']
+    names.sort(key=PP.natural_key)
+    assert names == ['CD4', 'CD45', 'chan1', 'chan2', 'chan10']
 
 
 def test_product_package_never_imports_the_oracle():
