@@ -27,6 +27,7 @@ SYMBOLS = [
     "pixie_map_data_to_nodes_host_f32", "pixie_map_data_to_nodes_host_f64",
     "pixie_label_histogram_i32", "pixie_scatter_labels_i16",
     "pixie_preprocess_workspace_bytes", "pixie_preprocess_fov_f64",
+    "pixie_column_quantile_workspace_bytes", "pixie_column_quantile_f64",
 ]
 
 _lib = None
@@ -102,6 +103,10 @@ def lib():
         L.pixie_preprocess_fov_f64.argtypes = [vp, i32, i32, i32, vp, vp, i32, dbl, vp, vp, vp, vp,
                                                i64, vp, vp, vp, vp, vp, sz, u32, vp]
         L.pixie_preprocess_fov_f64.restype = c.c_int
+        L.pixie_column_quantile_workspace_bytes.restype = sz
+        L.pixie_column_quantile_workspace_bytes.argtypes = [i32]
+        L.pixie_column_quantile_f64.argtypes = [vp, i64, i32, i64, dbl, vp, vp, vp, vp, sz, vp]
+        L.pixie_column_quantile_f64.restype = c.c_int
         L.pixie_label_histogram_i32.argtypes = [vp, vp, i64, i32, i32, vp, vp, vp]
         L.pixie_scatter_labels_i16.argtypes = [vp, vp, vp, i64, vp, i32, i32, i32, vp, vp, vp, vp]
         for name in ("pixie_label_histogram_i32", "pixie_scatter_labels_i16", "pixie_bmu_f32", "pixie_bmu_dist_f64", "pixie_cluster_sums_f32", "pixie_columns_to_rows_f32", "pixie_som_online_f64", "pixie_libc_sample_indices",

@@ -354,6 +354,25 @@ int pixie_preprocess_fov_f64(const void *img, int32_t H, int32_t W, int32_t C,
     return PIXIE_OK;
 }
 
+size_t pixie_column_quantile_workspace_bytes(int32_t C)
+{
+    return C < 1 ? 0 : pixie::quantile_workspace_bytes(C);
+}
+
+int pixie_column_quantile_f64(const double *X, int64_t n, int32_t C, int64_t ldX, double q,
+                              double *lo, double *hi, int64_t *m, void *workspace,
+                              size_t ws_bytes, void *stream)
+{
+    if (n < 0 || C < 1 || ldX < C || !(q >= 0.0 && q <= 1.0) || !lo || !hi || !m || (n > 0 && !X) ||
+        n >= ((int64_t)1 << 32) || n * (int64_t)C >= ((int64_t)1 << 40))
+        return PIXIE_ERR_INVALID_ARG;
+    if (!workspace || ws_bytes < pixie::quantile_workspace_bytes(C)) return PIXIE_ERR_WORKSPACE;
+    PX_CUDA(pixie::launch_column_quantile(X, n, C, ldX, q, lo, hi, m, workspace,
+                                          num_sms_current_device(),
+                                          reinterpret_cast<cudaStream_t>(stream)));
+    return PIXIE_OK;
+}
+
 int pixie_label_histogram_i32(const int32_t *seg_labels, const int32_t *clusters, int64_t n,
                               int32_t n_seg, int32_t n_clusters, int32_t *counts,
                               unsigned long long *out_of_range_or_null, void *stream)

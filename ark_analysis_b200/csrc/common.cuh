@@ -173,6 +173,11 @@ cudaError_t launch_preprocess(const void *img, int img_is_f64, int H, int W, int
                               int32_t *col_index, int32_t *labels_out, int64_t *n_kept,
                               int stop_after_blur, int num_sms, cudaStream_t stream);
 
+size_t quantile_workspace_bytes(int C);
+cudaError_t launch_column_quantile(const double *X, int64_t n, int C, int64_t ldX, double q,
+                                   double *lo, double *hi, int64_t *m_out, void *workspace,
+                                   int num_sms, cudaStream_t stream);
+
 size_t som_online_smem_bytes(int C, int K);
 cudaError_t launch_som_online(const float *X, int64_t n, int C, int64_t ldX, double *W, int xdim,
                               int ydim, const int64_t *sample_idx, int64_t niter,

@@ -123,3 +123,68 @@ def create_fov_pixel_data(fov, channels, img_data, seg_labels, pixel_thresh_val,
         pixel_mat['label'] = res["label"].cpu().numpy().astype(np.asarray(seg_labels).dtype)
     pixel_mat_subset = pixel_mat.sample(frac=subset_proportion)
     return pixel_mat, pixel_mat_subset
+
+
+# ------------------------------------------------------------------------------------------------
+# per-channel quantiles of the non-zero entries (reference pixie_preprocessing.py:405-410, :424-427)
+# ------------------------------------------------------------------------------------------------
+def _lerp(a, b, t):
+    """numpy's ``_lerp`` (the interpolation step of np.quantile / np.percentile, method 'linear')."""
+    diff = b - a
+    out = a + diff * t
+    hi = t >= 0.5
+    out[hi] = (b - diff * (1 - t))[hi]
+    return out
+
+
+def column_order_stats(X64, q):
+    """(lo, hi, m) per column of a CUDA float64 matrix [n, C]: the number m of valid entries
+    (non-zero, non-NaN) and the valid entries of rank floor((m-1) q) and that rank + 1 -- exact,
+    by radix select on the device (``pixie_column_quantile_f64``).  numpy arrays of length C."""
+    if not isinstance(X64, torch.Tensor) or not X64.is_cuda or X64.dtype != torch.float64 \
+            or X64.dim() != 2 or (X64.shape[1] > 1 and X64.stride(1) != 1):
+        raise PixieError("X64 must be a CUDA float64 matrix [n, C] with contiguous rows")
+    n, C = (int(v) for v in X64.shape)
+    dev = X64.device
+    lib = _native.lib()
+    lo = torch.empty(C, dtype=torch.float64, device=dev)
+    hi = torch.empty(C, dtype=torch.float64, device=dev)
+    m = torch.empty(C, dtype=torch.int64, device=dev)
+    ws = torch.empty(lib.pixie_column_quantile_workspace_bytes(C), dtype=torch.uint8, device=dev)
+    p = _som._ptr
+    with torch.cuda.device(dev):
+        rc = lib.pixie_column_quantile_f64(p(X64), n, C, X64.stride(0) if n > 1 else max(C, 1),
+                                           float(q), p(lo), p(hi), p(m), p(ws), ws.numel(),
+                                           _som._stream(dev))
+    _native.check(rc, "pixie_column_quantile_f64")
+    return lo.cpu().numpy(), hi.cpu().numpy(), m.cpu().numpy()
+
+
+def column_quantile(X64, q):
+    """``np.quantile(column[valid], q)`` (method 'linear') for every column, valid = non-zero and
+    non-NaN; NaN for a column without valid entries.  Bit-identical to numpy: the two order
+    statistics come from the device, the interpolation is numpy's own formula."""
+    q = np.float64(q)
+    lo, hi, m = column_order_stats(X64, q)
+    v = (m - 1).astype(np.float64) * q            # virtual index (n - 1) * q
+    gamma = v - np.floor(v)
+    with np.errstate(invalid="ignore"):
+        out = _lerp(lo, hi, gamma)
+    out[m == 0] = np.nan
+    return out
+
+
+def fov_channel_quantiles(X64, channels, q=0.999, name=None):
+    """The reference's per-FOV normalisation statistic
+    ``pixel_mat[channels].replace(0, np.nan).quantile(q=q, axis=0).rename(fov)``
+    (pixie_preprocessing.py:405-410) on the device-resident pixel matrix: a float64 Series indexed
+    by channel.  pandas < 3 hands ``q * 100`` to np.percentile, which divides by 100 again (that
+    can move q by one ulp, and the quantile by a few); pandas >= 3 calls np.quantile with q itself.
+    The installed pandas decides which of the two is reproduced."""
+    import pandas as pd
+    import pandas.core.array_algos.quantile as _pq
+    q_eff = np.float64(q)
+    if not hasattr(_pq, "_nanquantile"):      # the np.percentile route of pandas 1.x / 2.x
+        q_eff = np.true_divide(q_eff * 100.0, np.float64(100))
+    out = pd.Series(column_quantile(X64, q_eff), index=pd.Index(list(channels)), name=q if name is None else name)
+    return out

@@ -202,6 +202,21 @@ int pixie_preprocess_fov_f64(const void *img, int32_t H, int32_t W, int32_t C,
                              void *workspace, size_t ws_bytes, uint32_t flags, void *stream);
 
 /*
+ * N3, second half: the order statistics behind
+ *     fov_full_pixel_data.replace(0, np.nan).quantile(q, axis=0)
+ * (/root/reference/src/ark/phenotyping/pixie_preprocessing.py:405-410, :424-427), whose mean over
+ * the FOVs is the normalisation row of the SOM.  For every column c of X [n x C] fp64 (row pitch
+ * ldX): m[c] = number of valid entries (non-zero, non-NaN), lo[c] / hi[c] = the valid entries of
+ * rank floor((m-1) q) and that rank + 1 (clipped to the last rank), NaN when m = 0 -- exact (radix
+ * select, no sorting).  numpy's 'linear' quantile is lerp(lo, hi, (m-1) q - floor((m-1) q)); the
+ * caller does that on the host (ark_analysis_b200.pixie_preprocessing.column_quantile).
+ */
+size_t pixie_column_quantile_workspace_bytes(int32_t C);
+int pixie_column_quantile_f64(const double *X, int64_t n, int32_t C, int64_t ldX, double q,
+                              double *lo, double *hi, int64_t *m, void *workspace,
+                              size_t ws_bytes, void *stream);
+
+/*
  * N4 -- consumers of the label array.
  *
  * pixie_label_histogram_i32: counts[s * n_clusters + c] += 1 for every pixel i with

@@ -98,3 +98,20 @@ def preprocess_explicit(img, norm_vect, pixel_thresh_val, blur_factor, seg_label
     return {"blurred": b, "X64": X64, "X32": X64.astype(np.float32),
             "row_index": (ii // W).astype(np.int32), "column_index": (ii % W).astype(np.int32),
             "label": None if seg_labels is None else np.asarray(seg_labels).reshape(-1)[ii]}
+
+
+def fov_channel_quantiles(pixel_mat, channels, q=0.999):
+    """pixie_preprocessing.py:405-410: per-channel quantile of the non-zero entries, pandas' route."""
+    return pixel_mat[channels].replace(0, np.nan).quantile(q=q, axis=0)
+
+
+def column_quantile_explicit(X, q):
+    """numpy restatement per column: valid = non-zero, non-NaN; np.quantile(valid, q)."""
+    X = np.asarray(X, np.float64)
+    out = np.full(X.shape[1], np.nan)
+    for c in range(X.shape[1]):
+        v = X[:, c]
+        v = v[(v != 0) & ~np.isnan(v)]
+        if v.size:
+            out[c] = np.quantile(v, q)
+    return out

@@ -99,3 +99,39 @@ def test_full_fov_size_properties_and_device_handoff():
     lab = S.bmu(out["X32"], W0)
     torch.cuda.synchronize()
     assert lab.shape == (n,) and int(lab.min()) >= 1 and int(lab.max()) <= 100
+
+
+@pytest.mark.parametrize("q", [0.999, 0.5, 0.05, 0.0, 1.0, 0.3141])
+def test_column_quantile_matches_pandas_bit_for_bit(q, rng):
+    X = rng.random((5000, 9)) * np.array([1, 1e-3, 50, 1, 1, 1, 1, 1e-300, 1])
+    X[rng.random(X.shape) < 0.3] = 0
+    X[:, 3] = np.round(X[:, 3], 1)                 # heavy ties
+    X[:, 4] = 0                                    # no valid entry -> NaN
+    X[:, 5] = np.where(rng.random(5000) < 0.5, -X[:, 5], X[:, 5])   # negative values
+    X[:7, 6] = np.nan                              # NaN entries are skipped like zeros
+    X[1:, 8] = 0                                   # a single valid entry
+    chans = ['c%d' % i for i in range(9)]
+    ref = PO.fov_channel_quantiles(pd.DataFrame(X, columns=chans), chans, q)
+    got = PP.fov_channel_quantiles(torch.from_numpy(X).cuda(), chans, q)
+    np.testing.assert_array_equal(got.values, ref.values)
+    assert list(got.index) == chans
+    lo, hi, m = PP.column_order_stats(torch.from_numpy(X).cuda(), q)
+    np.testing.assert_array_equal(m, ((X != 0) & ~np.isnan(X)).sum(0))
+
+
+def test_quantiles_of_a_preprocessed_fov_and_edge_shapes(rng):
+    g = np.load(os.path.join(GOLD, "preprocess_48x40x8.npz"))
+    out = PP.preprocess_fov_device(g["img"], g["norm"], float(g["thresh"]), float(g["sigma"]))
+    chans = ['chan%d' % i for i in range(8)]
+    ref = PO.fov_channel_quantiles(pd.DataFrame(g["X64"], columns=chans), chans, 0.999)
+    got = PP.fov_channel_quantiles(out["X64"], chans, 0.999, name=0.999)
+    pd.testing.assert_series_equal(got, ref)
+    # empty matrix, one row, one column
+    assert np.isnan(PP.column_quantile(torch.empty((0, 3), dtype=torch.float64, device="cuda"), 0.5)).all()
+    one = torch.tensor([[0.25, 0.0, 3.0]], dtype=torch.float64, device="cuda")
+    np.testing.assert_array_equal(PP.column_quantile(one, 0.999), np.array([0.25, np.nan, 3.0]))
+    # full-size column set: 2^20 rows x 32 channels against np.quantile per column
+    X = torch.rand((1 << 20, 32), dtype=torch.float64, device="cuda")
+    X[X < 0.2] = 0
+    got = PP.column_quantile(X, 0.999)
+    np.testing.assert_array_equal(got, PO.column_quantile_explicit(X.cpu().numpy(), 0.999))

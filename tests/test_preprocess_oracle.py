@@ -55,3 +55,28 @@ def test_channel_names_sort_naturally():
     names = ['chan10', 'chan2', 'chan1', 'CD45', 'CD4']
     names.sort(key=PO._natural_key)
     assert names == ['CD4', 'CD45', 'chan1', 'chan2', 'chan10']
+
+
+def test_quantile_routes_agree_and_host_interpolation_is_numpys(rng):
+    """pandas' replace(0, nan).quantile against per-column np.quantile of the valid entries, and
+    the host-side interpolation the GPU path uses (order statistics + numpy's lerp formula) against
+    both -- bit for bit."""
+    import pandas as pd
+    from ark_analysis_b200.pixie_preprocessing import _lerp
+    X = rng.random((500, 6)) * np.array([1, 1e-3, 50, 1, 1, 1])
+    X[rng.random(X.shape) < 0.3] = 0
+    X[:, 4] = np.round(X[:, 4], 1)       # heavy ties
+    X[:, 5] = 0                          # no valid entry
+    chans = ['c%d' % i for i in range(6)]
+    df = pd.DataFrame(X, columns=chans)
+    for q in (0.999, 0.5, 0.05, 0.0, 1.0, 0.3141):
+        ref = PO.fov_channel_quantiles(df, chans, q).values
+        np.testing.assert_array_equal(PO.column_quantile_explicit(X, q), ref)
+        mine = np.full(6, np.nan)
+        for c in range(6):
+            v = np.sort(X[:, c][X[:, c] != 0])
+            if v.size:
+                vi = (v.size - 1) * np.float64(q)
+                r = min(int(np.floor(vi)), v.size - 1)
+                mine[c] = _lerp(v[r:r + 1], v[min(r + 1, v.size - 1):][:1], np.array([vi - np.floor(vi)]))[0]
+        np.testing.assert_array_equal(mine, ref)
