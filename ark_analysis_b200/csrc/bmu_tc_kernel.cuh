@@ -322,13 +322,21 @@ __device__ __noinline__ void step_update(const TcParams &p, int st, uint8_t *sme
         const int e0 = blockIdx.x * per;
         const int e1 = min(len, e0 + per);
         for (int e = e0 + tid; e < e1; e += nthr) {
-            double a = 0.0;
-            for (int r = 0; r < p.world; ++r) {
-                double v;
-                const double *src = p.peer_buf[r] + (size_t)(st & 1) * len + e;
-                asm volatile("ld.volatile.global.f64 %0, [%1];" : "=d"(v) : "l"(src) : "memory");
-                a += v;
+            // all ranks' values first (up to 8 NVLink round trips in flight together instead of one
+            // after the other), then the sum in rank order
+            double v[8];
+#pragma unroll
+            for (int r = 0; r < 8; ++r) {
+                v[r] = 0.0;
+                if (r < p.world) {
+                    const double *src = p.peer_buf[r] + (size_t)(st & 1) * len + e;
+                    asm volatile("ld.volatile.global.f64 %0, [%1];" : "=d"(v[r]) : "l"(src) : "memory");
+                }
             }
+            double a = 0.0;
+#pragma unroll
+            for (int r = 0; r < 8; ++r)
+                if (r < p.world) a += v[r];
             p.SN[e] = a;
         }
     }
