@@ -10,6 +10,11 @@ Public surface (mirrors the reference for this path and nothing else):
   ``generate_som_avg_files`` (reference: pixel_som_clustering.py)
 * ``ark_analysis_b200.cell_som_clustering``  -- ``train_cell_som`` / ``cluster_cells`` /
   ``generate_som_avg_files`` (reference: cell_som_clustering.py)
+* ``ark_analysis_b200.pixie_preprocessing``   -- ``create_fov_pixel_data`` / ``preprocess_fov_device`` /
+  ``fov_channel_quantiles`` (reference: pixie_preprocessing.py:18-80, :405-410)
+* ``ark_analysis_b200.cell_cluster_utils``    -- ``create_c2pc_data`` (reference:
+  cell_cluster_utils.py:63-192); ``ark_analysis_b200.data_utils`` -- ``generate_pixel_cluster_mask``
+  (reference: utils/data_utils.py:476-555)
 * ``ark_analysis_b200.compat.install()``     -- registers ``ark.phenotyping.*`` / ``pyFlowSOM``
   aliases so notebook cells written against the reference run unchanged.
 """

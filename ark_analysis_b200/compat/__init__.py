@@ -3,7 +3,9 @@ import resolve to this package --
 
 * ``pyFlowSOM`` (``som``, ``map_data_to_nodes``)  -> ``ark_analysis_b200.som``
 * ``ark.phenotyping.cluster_helpers`` / ``pixel_som_clustering`` / ``cell_som_clustering`` /
-  ``pixel_cluster_utils`` / ``cell_cluster_utils`` -> the modules of the same name here
+  ``pixel_cluster_utils`` / ``cell_cluster_utils`` / ``pixie_preprocessing`` and
+  ``ark.utils.data_utils`` -> the modules of the same name here (each holds only the functions of
+  the Pixie SOM path: SURVEY.md section 8)
 * ``feather`` (``read_dataframe``, ``write_dataframe``) -> ``ark_analysis_b200.io_utils``
 
 so ``templates/2_Pixie_Cluster_Pixels.ipynb`` cells 32/35 and the cell-clustering notebook run
@@ -16,7 +18,8 @@ import sys
 import types
 
 _ARK_MODULES = ["cluster_helpers", "pixel_som_clustering", "cell_som_clustering",
-                "pixel_cluster_utils", "cell_cluster_utils"]
+                "pixel_cluster_utils", "cell_cluster_utils", "pixie_preprocessing"]
+_ARK_UTILS = ["data_utils"]
 
 
 def _has_real(name):
@@ -59,4 +62,13 @@ def install(force=False):
             sys.modules[f"ark.phenotyping.{name}"] = mod
             setattr(phen, name, mod)
             done.append(f"ark.phenotyping.{name}")
+        utils = sys.modules.get("ark.utils") or types.ModuleType("ark.utils")
+        utils.__path__ = []
+        ark.utils = utils
+        sys.modules["ark.utils"] = utils
+        for name in _ARK_UTILS:
+            mod = importlib.import_module(f"ark_analysis_b200.{name}")
+            sys.modules[f"ark.utils.{name}"] = mod
+            setattr(utils, name, mod)
+            done.append(f"ark.utils.{name}")
     return done

@@ -145,6 +145,11 @@ def test_compat_aliases():
     from ark.phenotyping import cluster_helpers as ch
     assert pyFlowSOM.som is som.som and pyFlowSOM.map_data_to_nodes is som.map_data_to_nodes
     assert ch is cluster_helpers
+    # the rows either side of the SOM resolve under the reference's module names too
+    from ark.phenotyping import cell_cluster_utils as ccu, pixie_preprocessing as pp
+    from ark.utils import data_utils as du
+    assert callable(pp.create_fov_pixel_data) and callable(ccu.create_c2pc_data)
+    assert callable(du.generate_pixel_cluster_mask)
 
 
 def _make_pixel_dirs(base, fovs, chans, n=200, seed=0):
