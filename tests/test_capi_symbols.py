@@ -28,6 +28,49 @@ def test_library_builds_and_exports_every_declared_symbol():
     assert sorted(_native.SYMBOLS) == declared
 
 
+def header_prototypes():
+    """{name: [parameter type strings]} parsed from the header's declarations."""
+    text = open(os.path.join(ROOT, "include", "pixie_b200.h")).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    text = "\n".join(ln for ln in text.splitlines() if not ln.lstrip().startswith("#"))
+    out = {}
+    for m in re.finditer(r"\b(pixie_[a-z0-9_]+)\s*\(([^;{]*?)\)\s*;", text, flags=re.S):
+        params = [a.strip() for a in m.group(2).replace("\n", " ").split(",")]
+        out[m.group(1)] = [] if params in ([""], ["void"]) else params
+    return out
+
+
+def test_python_binding_matches_the_header_parameter_by_parameter():
+    """Every ctypes argtypes list has the header's arity and each parameter the header's kind
+    (pointer / 32-bit / 64-bit / double / size_t): a drifted binding would otherwise only show on
+    the GPU box."""
+    L = _native.lib()
+    protos = header_prototypes()
+    assert sorted(protos) == header_symbols()
+    c = ctypes
+
+    def kind(decl):
+        if "*" in decl:
+            return {c.c_void_p, c.c_char_p}
+        t = decl.rsplit(" ", 1)[0].replace("const", "").strip()
+        return {"int32_t": {c.c_int32}, "int": {c.c_int, c.c_int32}, "uint32_t": {c.c_uint32},
+                "int64_t": {c.c_int64}, "double": {c.c_double}, "size_t": {c.c_size_t},
+                "float": {c.c_float}}[t]
+
+    checked = 0
+    for name, params in protos.items():
+        fn = getattr(L, name)
+        if fn.argtypes is None:
+            assert not params or name in ("pixie_version", "pixie_device_count",
+                                          "pixie_kernel_launches"), name
+            continue
+        assert len(fn.argtypes) == len(params), (name, len(fn.argtypes), params)
+        for got, decl in zip(fn.argtypes, params):
+            assert got in kind(decl), (name, decl, got)
+        checked += 1
+    assert checked >= 15
+
+
 def test_version_error_strings_and_workspace_size():
     L = _native.lib()
     assert L.pixie_version() >= 100
