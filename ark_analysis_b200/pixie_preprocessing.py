@@ -13,7 +13,7 @@ import re
 import numpy as np
 import torch
 
-from . import _native
+from . import _native, io_utils
 from ._native import PixieError
 from . import som as _som
 
@@ -102,19 +102,9 @@ def preprocess_fov_device(img, norm_vect=None, pixel_thresh_val=0.0, blur_factor
     return out
 
 
-def create_fov_pixel_data(fov, channels, img_data, seg_labels, pixel_thresh_val,
-                          blur_factor=2, subset_proportion=0.1):
-    """The reference's ``create_fov_pixel_data``: (pixel_mat, pixel_mat_subset) for one FOV --
-    blurred, thresholded, row-normalised channel columns plus ``fov``, ``row_index``,
-    ``column_index`` (and ``label`` when ``seg_labels`` is given); the subset is
-    ``pixel_mat.sample(frac=subset_proportion)`` under numpy's global seed, as there.  Like the
-    reference, ``channels`` is sorted in place and ``img_data`` receives the blurred planes."""
+def _pixel_tables(res, fov, channels, seg_labels, subset_proportion):
+    """The two DataFrames of create_fov_pixel_data from the device results."""
     import pandas as pd
-    channels.sort(key=natural_key)
-    res = preprocess_fov_device(img_data, None, pixel_thresh_val, blur_factor, seg_labels,
-                                want_x64=True, want_x32=False)
-    if isinstance(img_data, np.ndarray) and img_data.dtype == np.float64 and img_data.flags.writeable:
-        img_data[...] = res["blurred"].cpu().numpy()
     pixel_mat = pd.DataFrame(res["X64"].cpu().numpy(), columns=channels)
     pixel_mat['fov'] = fov
     pixel_mat['row_index'] = res["row_index"].cpu().numpy().astype(np.int64)
@@ -123,6 +113,79 @@ def create_fov_pixel_data(fov, channels, img_data, seg_labels, pixel_thresh_val,
         pixel_mat['label'] = res["label"].cpu().numpy().astype(np.asarray(seg_labels).dtype)
     pixel_mat_subset = pixel_mat.sample(frac=subset_proportion)
     return pixel_mat, pixel_mat_subset
+
+
+def create_fov_pixel_data(fov, channels, img_data, seg_labels, pixel_thresh_val,
+                          blur_factor=2, subset_proportion=0.1):
+    """The reference's ``create_fov_pixel_data``: (pixel_mat, pixel_mat_subset) for one FOV --
+    blurred, thresholded, row-normalised channel columns plus ``fov``, ``row_index``,
+    ``column_index`` (and ``label`` when ``seg_labels`` is given); the subset is
+    ``pixel_mat.sample(frac=subset_proportion)`` under numpy's global seed, as there.  Like the
+    reference, ``channels`` is sorted in place and ``img_data`` receives the blurred planes."""
+    channels.sort(key=natural_key)
+    res = preprocess_fov_device(img_data, None, pixel_thresh_val, blur_factor, seg_labels,
+                                want_x64=True, want_x32=False)
+    if isinstance(img_data, np.ndarray) and img_data.dtype == np.float64 and img_data.flags.writeable:
+        img_data[...] = res["blurred"].cpu().numpy()
+    return _pixel_tables(res, fov, channels, seg_labels, subset_proportion)
+
+
+def _read_image(path):
+    from PIL import Image
+    with Image.open(path) as im:
+        return np.asarray(im)
+
+
+def load_fov_channels(tiff_dir, fov, channels, img_sub_folder=None):
+    """[H, W, C] stack of ``tiff_dir/fov/[img_sub_folder/]<channel>.tiff`` in the order of
+    ``channels`` -- the slice ``img_xr.loc[fov, :, :, channels]`` the reference takes from
+    alpineer's ``load_imgs_from_tree`` (pixie_preprocessing.py:131-154).  A channel without a file
+    is a ValueError, as the reference's verify_in_list makes it."""
+    import os
+    base = os.path.join(tiff_dir, fov, img_sub_folder) if img_sub_folder else os.path.join(tiff_dir, fov)
+    io_utils.validate_paths(base)
+    planes, missing = [], []
+    for ch in channels:
+        for ext in ('.tiff', '.tif'):
+            path = os.path.join(base, ch + ext)
+            if os.path.exists(path):
+                planes.append(_read_image(path))
+                break
+        else:
+            missing.append(ch)
+    if missing:
+        raise ValueError("Not all values given in list provided_chans were found in list "
+                         "pixel_mat_chans.\n Invalid values (first 10): " + ", ".join(missing[:10]))
+    return np.stack(planes, axis=-1)
+
+
+def preprocess_fov(base_dir, tiff_dir, data_dir, subset_dir, seg_dir, seg_suffix,
+                   img_sub_folder, is_mibitiff, channels, blur_factor,
+                   subset_proportion, pixel_thresh_val, seed, channel_norm_df, fov):
+    """The reference's ``preprocess_fov`` (pixie_preprocessing.py:83-185): load one FOV's channel
+    images (and its segmentation mask), normalise by ``channel_norm_df``, blur / filter / row-
+    normalise, write the full table to ``base_dir/data_dir/<fov>.feather`` and the sampled subset to
+    ``base_dir/subset_dir/<fov>.feather``, return the full table.  The float32 image and the
+    normalisation row go to the device as they are (the kernel divides in fp64, as numpy does for
+    float32 / float64); single-channel TIFFs only (MIBItiff containers are image IO, out of scope)."""
+    import os
+    if is_mibitiff:
+        raise NotImplementedError("MIBItiff containers are not read here: extract the channels to "
+                                  "single TIFFs (image IO is outside the Pixie SOM path)")
+    img = load_fov_channels(tiff_dir, fov, channels, img_sub_folder)
+    seg_labels = _read_image(os.path.join(seg_dir, fov + seg_suffix)) if seg_dir is not None else None
+    img_data = img.astype(np.float32)
+    norm_vect = np.array(channel_norm_df.iloc[0].values)
+    np.random.seed(seed)                       # the subset is drawn from numpy's global stream
+    channels.sort(key=natural_key)             # as create_fov_pixel_data does (names only)
+    res = preprocess_fov_device(img_data, norm_vect, pixel_thresh_val, blur_factor, seg_labels,
+                                want_x64=True, want_x32=False)
+    pixel_mat, pixel_mat_subset = _pixel_tables(res, fov, channels, seg_labels, subset_proportion)
+    io_utils.write_dataframe(pixel_mat, os.path.join(base_dir, data_dir, fov + ".feather"),
+                             compression='uncompressed')
+    io_utils.write_dataframe(pixel_mat_subset, os.path.join(base_dir, subset_dir, fov + ".feather"),
+                             compression='uncompressed')
+    return pixel_mat
 
 
 # ------------------------------------------------------------------------------------------------

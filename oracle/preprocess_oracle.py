@@ -115,3 +115,29 @@ def column_quantile_explicit(X, q):
         if v.size:
             out[c] = np.quantile(v, q)
     return out
+
+
+def preprocess_fov(base_dir, tiff_dir, data_dir, subset_dir, seg_dir, seg_suffix, img_sub_folder,
+                   channels, blur_factor, subset_proportion, pixel_thresh_val, seed,
+                   channel_norm_df, fov):
+    """pixie_preprocessing.py:83-185 for single-channel TIFF trees (PIL stands in for alpineer's
+    loader and skimage's imread): float32 image / float64 normalisation row, seeded subset, the two
+    uncompressed Feather files."""
+    import os
+
+    import pyarrow.feather as paf
+    from PIL import Image
+    sub = os.path.join(tiff_dir, fov, img_sub_folder) if img_sub_folder else os.path.join(tiff_dir, fov)
+    planes = [np.asarray(Image.open(os.path.join(sub, ch + '.tiff'))) for ch in channels]
+    seg = None if seg_dir is None else np.asarray(Image.open(os.path.join(seg_dir, fov + seg_suffix)))
+    img = np.stack(planes, axis=-1).astype(np.float32)
+    norm = np.array(channel_norm_df.iloc[0].values).reshape([1, 1, -1])
+    img = img / norm
+    np.random.seed(seed)
+    mat, sub_mat = create_fov_pixel_data(fov, channels, img, seg, pixel_thresh_val,
+                                         blur_factor=blur_factor,
+                                         subset_proportion=subset_proportion)
+    paf.write_feather(mat, os.path.join(base_dir, data_dir, fov + ".feather"), compression='uncompressed')
+    paf.write_feather(sub_mat, os.path.join(base_dir, subset_dir, fov + ".feather"),
+                      compression='uncompressed')
+    return mat

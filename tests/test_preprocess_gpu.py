@@ -135,3 +135,17 @@ def test_quantiles_of_a_preprocessed_fov_and_edge_shapes(rng):
     X[X < 0.2] = 0
     got = PP.column_quantile(X, 0.999)
     np.testing.assert_array_equal(got, PO.column_quantile_explicit(X.cpu().numpy(), 0.999))
+
+
+@pytest.mark.parametrize("with_seg,sub_dir", [(True, 'TIFs'), (False, None)])
+def test_preprocess_fov_writes_the_reference_files(with_seg, sub_dir, rng, tmp_path):
+    """preprocess_fov end to end on the GPU: both Feather files and the return value equal the
+    scipy + pandas route's (same rows sampled under the same seed)."""
+    import preprocess_fixtures as PF
+    out, chans = PF.run_both(str(tmp_path), rng, PP.preprocess_fov, PO.preprocess_fov,
+                             with_seg=with_seg, sub_dir=sub_dir)
+    (m_ret, m_full, m_sub), (o_ret, o_full, o_sub) = out['mirror'], out['oracle']
+    pd.testing.assert_frame_equal(m_full, o_full)
+    pd.testing.assert_frame_equal(m_sub, o_sub)
+    pd.testing.assert_frame_equal(m_ret, o_ret)
+    assert 0 < len(m_full) < 40 * 36

@@ -80,3 +80,42 @@ def test_quantile_routes_agree_and_host_interpolation_is_numpys(rng):
                 r = min(int(np.floor(vi)), v.size - 1)
                 mine[c] = _lerp(v[r:r + 1], v[min(r + 1, v.size - 1):][:1], np.array([vi - np.floor(vi)]))[0]
         np.testing.assert_array_equal(mine, ref)
+
+
+def _explicit_as_device_result(img, norm_vect=None, pixel_thresh_val=0.0, blur_factor=2,
+                               seg_labels=None, **_):
+    """TEST-ONLY stand-in for preprocess_fov_device: the explicit-order numpy restatement wrapped in
+    the result format of the device call (CPU tensors), so the HOST logic of the mirror -- file
+    layout, column order, seeding, Feather writes -- can be checked without a GPU.  The product
+    has no such route (test_host_logic.py checks it raises without a device)."""
+    import torch
+    r = PO.preprocess_explicit(img, norm_vect, pixel_thresh_val, blur_factor, seg_labels)
+    out = {k: torch.from_numpy(np.ascontiguousarray(v)) for k, v in r.items() if v is not None}
+    out["label"] = None if seg_labels is None else torch.from_numpy(np.ascontiguousarray(r["label"]))
+    out["n"] = len(r["X64"])
+    return out
+
+
+@pytest.mark.parametrize("with_seg,sub_dir", [(True, 'TIFs'), (False, None)])
+def test_preprocess_fov_host_logic_against_the_pandas_route(with_seg, sub_dir, rng, monkeypatch, tmp_path):
+    import pandas as pd
+    import preprocess_fixtures as PF
+    from ark_analysis_b200 import pixie_preprocessing as PP
+    monkeypatch.setattr(PP, "preprocess_fov_device", _explicit_as_device_result)
+    out, chans = PF.run_both(str(tmp_path), rng, PP.preprocess_fov, PO.preprocess_fov,
+                             with_seg=with_seg, sub_dir=sub_dir)
+    (m_ret, m_full, m_sub), (o_ret, o_full, o_sub) = out['mirror'], out['oracle']
+    pd.testing.assert_frame_equal(m_full, o_full)
+    pd.testing.assert_frame_equal(m_sub, o_sub)
+    pd.testing.assert_frame_equal(m_ret, o_ret)
+    assert list(m_full.columns[:3]) == chans and ('label' in m_full.columns) == with_seg
+    assert 0 < len(m_full) < 40 * 36 and len(m_sub) == round(0.1 * len(m_full))
+    assert np.all(m_full[chans].sum(axis=1) != 0)       # the reference test's own assertion
+    # the reference's error behaviour for this function
+    with pytest.raises(ValueError):
+        PP.load_fov_channels(str(tmp_path / 'sample_image_data'), 'fov0', ['chan0', 'nope'], sub_dir)
+    with pytest.raises(FileNotFoundError):
+        PP.load_fov_channels(str(tmp_path / 'sample_image_data'), 'fov9', ['chan0'], sub_dir)
+    with pytest.raises(NotImplementedError):
+        PP.preprocess_fov(str(tmp_path), str(tmp_path), 'a', 'b', None, '', None, True, chans, 2,
+                          0.1, 1.0, 42, None, 'fov0')
