@@ -11,6 +11,8 @@ import threading
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "_lib", "libpixie_b200.so")
+# experiments only: load another build of the same library (e.g. the `make prof` diagnostic build)
+_LIB_OVERRIDE = os.environ.get("PIXIE_LIB_PATH")
 CSRC = os.path.join(_HERE, "csrc")
 
 TILE = 128
@@ -20,10 +22,11 @@ STAT_ROWS_FLAGGED, STAT_PAIRS, STAT_ROWS_FP64, STAT_ROWS_FIXUP, STAT_KERNEL = 0,
 
 # every symbol include/pixie_b200.h declares (checked by tests/test_capi_symbols.py)
 SYMBOLS = [
-    "pixie_version", "pixie_error_string", "pixie_kernel_launches", "pixie_device_count", "pixie_workspace_bytes",
+    "pixie_version", "pixie_error_string", "pixie_kernel_launches", "pixie_device_count", "pixie_debug_trace", "pixie_workspace_bytes",
     "pixie_bmu_f32", "pixie_bmu_dist_f64", "pixie_cluster_sums_f32", "pixie_columns_to_rows_f32", "pixie_som_online_f64", "pixie_libc_sample_indices",
     "pixie_som_accum_f32", "pixie_som_apply_f64",
-    "pixie_som_train_f32", "pixie_peer_buffer_bytes", "pixie_som_train_peers_f32",
+    "pixie_som_train_f32", "pixie_peer_buffer_bytes", "pixie_som_train_peers_supported",
+    "pixie_som_train_peers_f32",
     "pixie_map_data_to_nodes_host_f32", "pixie_map_data_to_nodes_host_f64",
     "pixie_label_histogram_i32", "pixie_scatter_labels_i16",
     "pixie_preprocess_workspace_bytes", "pixie_preprocess_fov_f64",
@@ -68,7 +71,7 @@ def lib():
                 f"{LIB_PATH} is missing: the CUDA extension was not built "
                 "(run `python -c 'import __graft_entry__ as g; g.build()'`). "
                 "There is no CPU fallback for the Pixie SOM path.")
-        L = ctypes.CDLL(LIB_PATH)
+        L = ctypes.CDLL(_LIB_OVERRIDE or LIB_PATH)
         c = ctypes
         vp, i32, i64, u32, dbl, sz = c.c_void_p, c.c_int32, c.c_int64, c.c_uint32, c.c_double, \
             c.c_size_t
@@ -76,6 +79,8 @@ def lib():
         L.pixie_error_string.restype = c.c_char_p
         L.pixie_error_string.argtypes = [c.c_int]
         L.pixie_device_count.restype = c.c_int
+        L.pixie_debug_trace.restype = c.c_int
+        L.pixie_debug_trace.argtypes = [vp, c.c_int]
         L.pixie_kernel_launches.restype = c.c_ulonglong
         L.pixie_workspace_bytes.restype = sz
         L.pixie_workspace_bytes.argtypes = [i64, i32, i32]
@@ -93,6 +98,8 @@ def lib():
                                           dbl, dbl, dbl, vp, sz, u32, vp]
         L.pixie_peer_buffer_bytes.restype = sz
         L.pixie_peer_buffer_bytes.argtypes = [i32, i32]
+        L.pixie_som_train_peers_supported.restype = c.c_int
+        L.pixie_som_train_peers_supported.argtypes = [i32, i32, i64, i32]
         L.pixie_som_train_peers_f32.argtypes = [vp, i64, i32, i64, vp, vp, vp, i32, i32, i32, i32, dbl,
                                                 dbl, dbl, dbl, i64, i32, i32, vp, u32, vp, sz, u32, vp]
         L.pixie_som_train_peers_f32.restype = c.c_int

@@ -29,6 +29,14 @@ def _has_real(name):
         return False
 
 
+def shim_path():
+    """Directory of the stand-in modules (feather, natsort, alpineer, skimage.io, pyFlowSOM) that
+    let the UNMODIFIED reference modules import in an image without those packages.  Append it to
+    ``sys.path`` (after site-packages, so a really installed package wins)."""
+    import os
+    return os.path.join(os.path.dirname(os.path.abspath(__file__)), "shims")
+
+
 def install(force=False):
     """Register the aliases in ``sys.modules``.  Returns the list of names registered."""
     from .. import io_utils, som

@@ -29,6 +29,7 @@
 #include <stdlib.h>
 
 #include "bmu_tc_kernel.cuh"
+#include "som_update.cuh"
 
 namespace pixie {
 
@@ -90,16 +91,37 @@ TcPlan make_tc_plan(int C, int K, bool acc)
         p.wimg_bytes = p.off_bias + (uint32_t)p.Ntot * 32u;
         p.off_ones = (p.wimg_bytes + 1023u) / 1024u * 1024u;
         p.off_x = p.off_ones + 4096u;
-        // fused accumulation: one fp32 table per epilogue group + the group's sort scratch
-        if (acc && C + 1 > 128) continue;  // the side-buffer merge: one thread of the group per column
-        const uint32_t sort_bytes = sort_layout(C, K).bytes;
-        const uint32_t acc_bytes =
-            acc ? ((uint32_t)v.NG * (uint32_t)K * (uint32_t)(C + 1) * 4u + 15u) / 16u * 16u +
-                      (uint32_t)v.NG * sort_bytes
-                : 0u;
+        // fused accumulation: the groups' node counts and label rings (the tables themselves live
+        // in global memory); the pair-list area doubles as the accumulate lists and as scratch of
+        // the end-of-step update (som_update_nodes) and of the cross-GPU exchange
         const uint32_t pair_cap = acc ? kWarpPairCapAcc : kWarpPairCap;
-        const uint32_t scratch = (uint32_t)kBarBlock + (uint32_t)(4 * v.NG) * pair_cap * 8u + acc_bytes;
+        uint32_t pairs_bytes = (uint32_t)(4 * v.NG) * pair_cap * 8u;
+        if (acc) {
+            uint32_t need = som_update_scratch_bytes(C, K);
+            const uint32_t slice = (uint32_t)((K * (C + 1) + kSumParts - 1) / kSumParts) * 8u;
+            if (slice > need) need = slice;
+            if (need > pairs_bytes) pairs_bytes = (need + 15u) / 16u * 16u;
+        }
         const uint32_t limit = 227u * 1024u - 1024u;
+        const uint32_t tables = (uint32_t)v.NG * (uint32_t)K * (uint32_t)tab_pitch(C) * 4u;
+        const uint32_t counts = ((uint32_t)v.NG * (uint32_t)K * 4u + 15u) / 16u * 16u;
+        const uint32_t rings = (uint32_t)v.NG * 512u;
+        uint32_t acc_bytes = 0;
+        p.tab_global = 0;
+        if (acc) {
+            const uint32_t fixed = p.off_x + (uint32_t)kBarBlock + pairs_bytes + counts + rings +
+                                   (uint32_t)v.NG * p.stage_bytes;
+            const int force = env_int("PIXIE_TAB_GLOBAL", -1);
+            const bool fits = fixed + tables <= limit;
+            if (force == 1 || !fits) {
+                if (force == 0) continue;
+                p.tab_global = 1;
+                acc_bytes = counts + rings;
+            } else {
+                acc_bytes = tables + counts + rings;
+            }
+        }
+        const uint32_t scratch = (uint32_t)kBarBlock + pairs_bytes + acc_bytes;
         if (p.off_x + scratch + (uint32_t)v.NG * p.stage_bytes > limit) continue;
         p.nstage = (int)((limit - p.off_x - scratch) / p.stage_bytes);
         if (p.nstage > kMaxStages) p.nstage = kMaxStages;
@@ -112,14 +134,15 @@ TcPlan make_tc_plan(int C, int K, bool acc)
         p.off_bar = p.off_x + (uint32_t)p.nstage * p.stage_bytes;
         p.off_pairs = p.off_bar + (uint32_t)kBarBlock;
         p.pair_cap = (int)pair_cap;
-        p.off_acc = p.off_pairs + (uint32_t)(4 * v.NG) * pair_cap * 8u;
-        p.off_lab = p.off_acc + (acc_bytes ? acc_bytes - (uint32_t)v.NG * sort_bytes : 0u);
-        p.sort_stride = sort_bytes;
+        p.pairs_bytes = pairs_bytes;
+        p.off_acc = p.off_pairs + pairs_bytes;
+        p.off_cnt = p.off_acc + ((acc && !p.tab_global) ? tables : 0u);
+        p.off_lab = p.off_cnt + (acc ? counts : 0u);
         p.acc = acc ? 1 : 0;
         p.smem_bytes = p.off_acc + acc_bytes + 1024u;
         p.ok = true;
         // fewest padded codebook rows first; then more epilogue groups; then deeper pipeline
-        const long cost = (long)(p.Nchunk * v.NCH) * 1000 - v.NG * 10 - p.nstage;
+        const long cost = (long)(p.Nchunk * v.NCH) * 1000 - v.NG * 10 - p.nstage + (p.tab_global ? 15 : 0);
         if (best_cost < 0 || cost < best_cost) {
             best_cost = cost;
             best = p;

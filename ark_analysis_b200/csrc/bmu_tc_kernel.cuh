@@ -2,13 +2,63 @@
 // by the bmu_tc_inst_*.cu translation units, each of which instantiates one family of variants.
 #pragma once
 #include <float.h>
+#include <stdio.h>
 
 #include "common.cuh"
 #include "ptx.cuh"
+#include "som_update.cuh"
+
+// Tile-phase cycle counters of warp 0 of CTA 0 (diagnostic builds: make prof).  They live in
+// registers and reach the control block once per step, so that reading them does not stall the
+// phases they measure.
+#ifdef PIXIE_PROFILE
+#define PIXIE_PROF_DECL() long long prof_[8] = {0, 0, 0, 0, 0, 0, 0, 0}; long long tick_ = 0; unsigned int trace_n_ = 0
+#define PIXIE_TICK(i) tick_ = clock64()
+#define PIXIE_TOCK(i)                     \
+    do {                                  \
+        const long long now_ = clock64(); \
+        prof_[i] += now_ - tick_;         \
+        tick_ = now_;                     \
+    } while (0)
+#define PIXIE_TILE_DONE() prof_[6] += 1
+#define PIXIE_PROF_FLUSH()                                                          \
+    do {                                                                            \
+        if (blockIdx.x == 0 && threadIdx.x == 0) {                                  \
+            for (int i_ = 0; i_ < 8; ++i_) {                                        \
+                p.ctl->tile_cyc[i_] += (unsigned long long)prof_[i_];               \
+                prof_[i_] = 0;                                                      \
+            }                                                                       \
+        }                                                                           \
+    } while (0)
+// event trace of CTA 0 (one lane per warp): {step, warp, event, tile seq} + globaltimer
+#define PIXIE_TRACE(ev, seq_)                                                                   \
+    do {                                                                                        \
+        if (p.trace && blockIdx.x == 0 && (threadIdx.x & 31) == 0 && st >= p.dbg_step0 &&       \
+            st < p.dbg_step0 + 2 && trace_n_ < 1024u) {                                         \
+            /* every warp owns 1024 slots: no atomics, the two stores are fire-and-forget */    \
+            unsigned long long *slot_ = p.trace + 2u * ((threadIdx.x >> 5) * 1024u + trace_n_); \
+            slot_[0] = ((unsigned long long)st << 48) | ((unsigned long long)(threadIdx.x >> 5) << 40) | \
+                       ((unsigned long long)(ev) << 32) | (unsigned int)(seq_);                 \
+            slot_[1] = global_timer_ns();                                                       \
+            ++trace_n_;                                                                         \
+        }                                                                                       \
+    } while (0)
+#else
+#define PIXIE_TRACE(ev, seq_)
+#define PIXIE_PROF_DECL()
+#define PIXIE_TICK(i)
+#define PIXIE_TOCK(i)
+#define PIXIE_TILE_DONE()
+#define PIXIE_PROF_FLUSH()
+#endif
 
 namespace pixie {
 
 using namespace ptx;
+
+#ifdef PIXIE_PROFILE
+constexpr unsigned int kTraceCap = 1u << 15;
+#endif
 
 // Image layout (bytes): block b (32 columns) at b * Ntot * 128, row r at r * 128, 16-byte chunk c at
 // ((c ^ (r & 7)) << 4) -- exactly what TMA SWIZZLE_128B would have written, so one linear
@@ -179,23 +229,45 @@ static __device__ __noinline__ double pair_dist_f64(const uint8_t *xs, const uin
     return __dsqrt_rn(acc);
 }
 
-// Grid-wide barrier for the persistent kernel (every CTA is resident: grid <= SM count and one CTA
-// per SM fits).  `counter` only ever grows during a launch; `target` is the value it reaches when
-// all CTAs have arrived at this barrier instance.
-__device__ __forceinline__ void grid_barrier(unsigned int *counter, unsigned int target)
+// ------------------------------------------------------------------------------------------------
+// train mode (ACC variants): synchronisation
+// ------------------------------------------------------------------------------------------------
+// The TMA producer warp never takes part in the end-of-step work: X does not depend on the
+// codebook, so it keeps streaming the NEXT step's tiles into free stages while the other warps
+// (epilogue groups + MMA warp, `nthr` threads) fold, exchange and update.  Those warps meet at
+// named barrier kBarStep.
+constexpr uint32_t kBarStep = 8;
+
+__device__ __forceinline__ unsigned int ld_acquire_gpu(const unsigned int *p)
 {
-    __threadfence();
-    __syncthreads();
-    if (threadIdx.x == 0) {
+    unsigned int v;
+    asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+
+// Grid-wide barrier (every CTA is resident: cooperative launch, grid <= SM count).  `counter` only
+// grows during a launch; `target` is its value once every CTA has arrived at this instance.  One
+// thread per CTA talks to L2; the CTA barriers on both sides make its fences cumulative for the
+// whole CTA (the scheme cooperative groups uses).
+__device__ __forceinline__ void grid_barrier(unsigned int *counter, unsigned int target,
+                                             uint32_t nthr, bool leader)
+{
+    bar_sync(kBarStep, nthr);
+    if (leader) {
+        __threadfence();
         atomicAdd(counter, 1u);
         unsigned spins = 0;
-        while (*reinterpret_cast<volatile unsigned int *>(counter) < target) {
-            __nanosleep(32);
-            if (++spins > (1u << 25)) __trap();  // seconds: never on a healthy launch
+        uint64_t t0 = 0;
+        while (ld_acquire_gpu(counter) < target) {
+            if ((++spins & 1023u) == 0u) {  // a wedged grid traps after ~4 s instead of hanging
+                const uint64_t now = global_timer_ns();
+                if (t0 == 0) t0 = now;
+                if (now - t0 > 4000000000ull) __trap();
+            }
         }
         __threadfence();
     }
-    __syncthreads();
+    bar_sync(kBarStep, nthr);
 }
 
 // tiles of one mini-batch step that this shard holds: local tiles first, first + B, ... whose
@@ -221,21 +293,299 @@ __device__ __forceinline__ StepTiles step_tiles(const TcParams &p, int st)
 }
 
 // ------------------------------------------------------------------------------------------------
-// whole-pass mode, end of a step: fold the CTAs' sums, apply the batch update (DESIGN.md section 4,
-// same arithmetic as som_apply_kernel) and rewrite the codebook image for the next step.
-// Called by every thread of every CTA; three grid barriers.
+// train mode: the per-node statistics.  Each epilogue group owns a private table of channel sums
+// -- in shared memory ([K][tab_pitch(C)] fp32) when NG of them fit beside the pipeline, else in
+// global memory (L2-resident: [K][part_pitch(C)], group g of CTA b is table b * NG + g of
+// p.partials) -- and an int32 count per node in shared memory.
+//
+// publish_labels: the tile's labels go to the group's ring (two slots: a warp may start the next
+// tile while a sibling still reads this one's) and every row counts itself (integer shared-memory
+// atomic: order-free); then the four warps of the group meet.
+//
+// tile_accumulate: warp `quad` owns the nodes with (node & 3) == quad.  It compacts the tile's rows
+// of those nodes (ascending row order) into a list and walks it FOUR ROWS PER INSTRUCTION: lane =
+// (row of the batch, 16-byte chunk of the 128-byte row), so one 128-bit access moves four rows of
+// 32 channels.  No other warp, group or CTA touches this warp's table rows, and the adds into a
+// cell happen in list order: the sums are deterministic.
+//   shared table: 128-bit read-modify-write; rows of one node inside a batch go in turn
+//   global table: red.global.add.v4.f32, fire and forget (L2 performs ~1 fp32 atomic per clock
+//                 and slice: fine for the big shapes that have no room on chip, but at cfg2 the
+//                 5.4 M atomics of a step take longer to drain than the step's tiles take)
+//
+// What this costs is instructions: a warp runs it serially once per tile.  History (cfg2, us per
+// tile): counting sort + segment walk 3.5; one row per instruction with counts in registers 3.3
+// (950 instructions); 128-bit lanes with an all-or-nothing serial fallback 4+ (63 % of the
+// four-row batches hold a duplicate node); rows dealt into four hazard-free lists: costs more
+// to build than it saves.
 // ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void publish_labels(uint8_t *smem, uint32_t lab_off, int *cnt_s, int K,
+                                               int g, int quad, int lane, int L, uint32_t parity)
+{
+    uint16_t *lab = reinterpret_cast<uint16_t *>(smem + lab_off) + parity * 128u;
+    lab[quad * 32 + lane] = (uint16_t)L;
+    if (L < K) atomicAdd(cnt_s + L, 1);
+    bar_sync(1u + (uint32_t)g, 128);
+}
+
+template <int NBLK, bool TABG>
+__device__ __forceinline__ void tile_accumulate_blk(const TcParams &p, uint8_t *smem,
+                                                    uint32_t xs_addr, uint32_t tab_addr,
+                                                    float *tab_g, uint32_t lab_off,
+                                                    uint32_t list_addr, int quad, int lane,
+                                                    uint32_t parity)
+{
+    const TcPlan &pl = p.plan;
+    const int K = pl.K, C = pl.C;
+    const uint32_t pitch4 = (uint32_t)(TABG ? part_pitch(C) : tab_pitch(C)) * 4u;
+    const uint16_t *lab = reinterpret_cast<const uint16_t *>(smem + lab_off) + parity * 128u;
+    // 1. this warp's rows as a compact list of 8-byte entries {row * 128 | (row & 7) << 4,
+    //    node * pitch bytes} (the list lives in the warp's idle pair buffer: 128 x 8 bytes)
+    const uint32_t lt = (1u << lane) - 1u;
+    uint32_t total = 0;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        const uint32_t l = lab[j * 32 + lane];
+        const bool mine = (int)l < K && (int)(l & 3u) == quad;
+        const uint32_t m = __ballot_sync(0xffffffffu, mine);
+        if (mine) {
+            const uint32_t row = (uint32_t)(j * 32 + lane);
+            const uint32_t pos = total + (uint32_t)__popc(m & lt);
+            asm volatile("st.shared.v2.u32 [%0], {%1, %2};" ::"r"(list_addr + pos * 8u),
+                         "r"(row * 128u | (row & 7u) << 4), "r"(l * pitch4)
+                         : "memory");
+        }
+        total += (uint32_t)__popc(m);
+    }
+    __syncwarp();
+    // 2. the walk.  Physical address of chunk ck of tile row r in a 32-channel block:
+    //    (block + r * 128 + ck * 16) ^ ((r & 7) << 4)  (SWIZZLE_128B).
+    const uint32_t r4 = (uint32_t)lane >> 3, ck = (uint32_t)lane & 7u;
+    const uint32_t A = xs_addr + ck * 16u;
+    const bool last_ok = (NBLK - 1) * 32 + (int)ck * 4 < C;  // the last block may be partial
+    auto ldsf4 = [](uint32_t addr) {
+        float4 v;
+        asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];"
+                     : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w)
+                     : "r"(addr));
+        return v;
+    };
+    const uint32_t my = list_addr + r4 * 8u;
+    if constexpr (TABG) {
+        // global table: fire and forget, nothing to order
+        char *const G = reinterpret_cast<char *>(tab_g) + ck * 16u;
+        auto add_row = [&](uint32_t w0, uint32_t w1) {
+            const uint32_t xa = (A ^ (w0 & 0x70u)) + (w0 & 0xFFFFFF80u);
+            char *cell = G + w1;
+#pragma unroll
+            for (int blk = 0; blk < NBLK; ++blk) {
+                if (blk < NBLK - 1 || last_ok) {
+                    const float4 x = ldsf4(xa + (uint32_t)blk * 16384u);
+                    asm volatile("red.relaxed.gpu.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(
+                                     cell + blk * 128),
+                                 "f"(x.x), "f"(x.y), "f"(x.z), "f"(x.w)
+                                 : "memory");
+                }
+            }
+        };
+        const uint32_t full = total & ~3u;
+        for (uint32_t i = 0; i < full; i += 4u) {
+            uint32_t w0, w1;
+            asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(w0), "=r"(w1) : "r"(my + i * 8u));
+            add_row(w0, w1);
+        }
+        if (full + r4 < total) {  // the last, short batch
+            uint32_t w0, w1;
+            asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(w0), "=r"(w1) : "r"(my + full * 8u));
+            add_row(w0, w1);
+        }
+    } else {
+        // shared table: read-modify-write.  Rows of one node inside a batch must go one after the
+        // other: rank = how many EARLIER rows of the batch share my node (one match.any); round r
+        // takes the rows of rank r.  Most batches need one or two rounds.
+        const uint32_t T = tab_addr + ck * 16u;
+        const uint32_t below = (1u << (r4 * 8u)) - 1u;
+        auto rmw = [&](uint32_t xa, uint32_t ta) {
+            float4 x[NBLK], t[NBLK];
+#pragma unroll
+            for (int blk = 0; blk < NBLK; ++blk)
+                if (blk < NBLK - 1 || last_ok) x[blk] = ldsf4(xa + (uint32_t)blk * 16384u);
+#pragma unroll
+            for (int blk = 0; blk < NBLK; ++blk)
+                if (blk < NBLK - 1 || last_ok) t[blk] = ldsf4(ta + (uint32_t)blk * 128u);
+#pragma unroll
+            for (int blk = 0; blk < NBLK; ++blk)
+                if (blk < NBLK - 1 || last_ok)
+                    asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(ta + (uint32_t)blk * 128u),
+                                 "f"(t[blk].x + x[blk].x), "f"(t[blk].y + x[blk].y),
+                                 "f"(t[blk].z + x[blk].z), "f"(t[blk].w + x[blk].w)
+                                 : "memory");
+        };
+        for (uint32_t i = 0; i < total; i += 4u) {
+            const bool on = i + r4 < total;  // the last batch may be short
+            uint32_t w0 = 0u, w1 = 0x80000000u | r4;  // an idle lane group matches nobody
+            if (on)
+                asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(w0), "=r"(w1) : "r"(my + i * 8u));
+            const unsigned same = __match_any_sync(0xffffffffu, w1);
+            const int rank = __popc(same & below) >> 3;
+            const uint32_t xa = (A ^ (w0 & 0x70u)) + (w0 & 0xFFFFFF80u), ta = T + w1;
+            if (on && rank == 0) rmw(xa, ta);
+            if (__any_sync(0xffffffffu, rank >= 1)) {
+                __syncwarp();
+                if (on && rank == 1) rmw(xa, ta);
+                if (__any_sync(0xffffffffu, rank >= 2)) {
+                    __syncwarp();
+                    if (on && rank == 2) rmw(xa, ta);
+                    __syncwarp();
+                    if (on && rank == 3) rmw(xa, ta);
+                }
+                __syncwarp();
+            }
+        }
+    }
+    __syncwarp();  // the list is the warp's pair buffer again from the next tile on
+}
+
+__device__ __forceinline__ void tile_accumulate(const TcParams &p, uint8_t *smem, uint32_t xs_addr,
+                                                uint32_t tab_addr, float *tab_g, uint32_t lab_off,
+                                                uint32_t list_addr, int quad, int lane,
+                                                uint32_t parity)
+{
+    // warp-uniform dispatch: the block loop is unrolled and the table kind fixed per case
+#define PIXIE_ACC_CASE(n_)                                                                        \
+    case n_:                                                                                      \
+        if (tab_g != nullptr)                                                                     \
+            tile_accumulate_blk<n_, true>(p, smem, xs_addr, tab_addr, tab_g, lab_off, list_addr,  \
+                                          quad, lane, parity);                                    \
+        else                                                                                      \
+            tile_accumulate_blk<n_, false>(p, smem, xs_addr, tab_addr, tab_g, lab_off, list_addr, \
+                                           quad, lane, parity);                                   \
+        break;
+    switch (p.plan.nblkX) {
+        PIXIE_ACC_CASE(1)
+        PIXIE_ACC_CASE(2)
+        PIXIE_ACC_CASE(3)
+        default:
+        PIXIE_ACC_CASE(4)
+    }
+#undef PIXIE_ACC_CASE
+}
+
+// ------------------------------------------------------------------------------------------------
+// train mode, end of a step (called by the `nthr` non-producer threads of every CTA, tid < nthr):
+//   1. [shared tables] the NG group tables are added in group order into the CTA's part of
+//      p.partials and cleared; [global tables] they already are parts
+//   2. grid barrier; every CTA folds ITS slice of the K x (C+1) table over all parts, part order,
+//      fp64 (global tables are cleared by the thread that just read them)
+//   3. [N > 1] cross-GPU sum over NVLink peer memory: see exchange_slice()
+//   4. grid barrier; batch update (som_update_nodes), CTA j takes nodes j, j + grid, ...: W64, W32,
+//      the codebook image rows and the norms of the next step; grid barrier
+// Without p.apply (one step per launch: pixie_som_accum_f32) it stops after the fold.
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void fold_slice_sum(const TcParams &p, int nparts, int len, int e0,
+                                               int e1, int per, int tid, int nthr, double *dst)
+{
+    const int ld = p.plan.C + 1, ldp = part_pitch(p.plan.C);
+    const size_t plen = (size_t)p.plan.K * ldp;  // floats per part
+    const int oct = tid >> 3, q = tid & 7, noct = nthr >> 3;
+    const int rounds = (per + noct - 1) / noct;  // uniform trip count: shuffles below
+    for (int it = 0; it < rounds; ++it) {
+        const int e = e0 + it * noct + oct;  // logical element (node k, column c) of K x (C+1)
+        double a = 0.0;
+        if (e < e1) {
+            const int k = e / ld, c = e - k * ld;
+            const float *col = p.parts + (size_t)k * ldp + c;
+            // thread q of the octet sums parts q, q + 8, ... (ascending), eight loads in flight
+            for (int pp = q; pp < nparts; pp += 64) {
+                float v[8];
+#pragma unroll
+                for (int u = 0; u < 8; ++u)
+                    v[u] = pp + 8 * u < nparts ? __ldcg(col + (size_t)(pp + 8 * u) * plen) : 0.f;
+#pragma unroll
+                for (int u = 0; u < 8; ++u) a += (double)v[u];
+            }
+        }
+        a += __shfl_xor_sync(0xffffffffu, a, 1);
+        a += __shfl_xor_sync(0xffffffffu, a, 2);
+        a += __shfl_xor_sync(0xffffffffu, a, 4);
+        if (e < e1 && q == 0) dst[e - e0] = a;
+    }
+}
+
+// Cross-GPU sum of this CTA's slice [e0, e1) (s_slice holds this rank's folded values).
+// Exchange buffer of a rank (torch symmetric memory, mapped on every rank):
+//   vals  double [2][8][len]        parity of the step x SOURCE rank x element
+//   flags uint32 [2][8][kSumParts]  parity x source rank x slice (= CTA) index
+// Every CTA PUSHES its slice into the vals[parity][my rank] area of every rank (plain remote stores:
+// one-way NVLink traffic, no round trip), then raises flags[parity][my rank][cta] on every rank
+// (fence.sys + store); it then waits for the same flag from every source rank in its OWN buffer
+// (local polls) and adds the eight slices in rank order -- every rank adds the same values in the
+// same order: bit-identical totals, no grid barrier, no NCCL call, no host round trip.
+// Reuse of a parity slot two steps later is safe: a rank can only reach the push of step t + 2
+// after it saw this rank's flag of step t + 1, which this CTA raised after it had read step t.
+__device__ __forceinline__ void exchange_slice(const TcParams &p, int st, int len, int e0, int e1,
+                                               int tid, int nthr, const double *s_slice)
+{
+    const int par = st & 1;
+    const size_t vals_off = ((size_t)par * 8 + (size_t)p.rank) * len;
+    for (int i = tid; i < (e1 - e0) * p.world; i += nthr) {
+        const int r = i / (e1 - e0), e = e0 + (i - r * (e1 - e0));
+        double *dst = p.peer_buf[r] + vals_off + e;
+        asm volatile("st.relaxed.sys.global.f64 [%0], %1;" ::"l"(dst), "d"(s_slice[e - e0]) : "memory");
+    }
+    bar_sync(kBarStep, nthr);
+    const uint32_t val = p.flag_base + (uint32_t)st + 1u;
+    const size_t flags_off = (size_t)2 * 8 * len * sizeof(double);
+    if (tid < p.world) {
+        __threadfence_system();
+        uint32_t *dst = reinterpret_cast<uint32_t *>(reinterpret_cast<char *>(p.peer_buf[tid]) + flags_off) +
+                        ((size_t)par * 8 + p.rank) * kSumParts + blockIdx.x;
+        asm volatile("st.relaxed.sys.global.u32 [%0], %1;" ::"l"(dst), "r"(val) : "memory");
+        const uint32_t *src = reinterpret_cast<const uint32_t *>(
+                                  reinterpret_cast<const char *>(p.peer_buf[p.rank]) + flags_off) +
+                              ((size_t)par * 8 + tid) * kSumParts + blockIdx.x;
+        uint32_t seen, spins = 0;
+        uint64_t t0 = 0;
+        do {
+            asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(seen) : "l"(src) : "memory");
+            if (seen - val < 0x80000000u) break;  // seen >= val (wrap-safe)
+            if ((++spins & 1023u) == 0u) {
+                // a peer that never arrives (died, or took the other code path) makes this rank
+                // fail after 60 s instead of hanging; launch skew between ranks is far below that
+                const uint64_t now = global_timer_ns();
+                if (t0 == 0) t0 = now;
+                if (now - t0 > 60000000000ull) __trap();
+                __nanosleep(128);
+            }
+        } while (true);
+    }
+    bar_sync(kBarStep, nthr);
+    const double *mine = p.peer_buf[p.rank] + (size_t)par * 8 * len;
+    for (int e = e0 + tid; e < e1; e += nthr) {
+        double v[8];
+#pragma unroll
+        for (int r = 0; r < 8; ++r) {
+            v[r] = 0.0;
+            if (r < p.world)
+                asm volatile("ld.relaxed.sys.global.f64 %0, [%1];" : "=d"(v[r]) : "l"(mine + (size_t)r * len + e) : "memory");
+        }
+        double a = 0.0;
+#pragma unroll
+        for (int r = 0; r < 8; ++r)
+            if (r < p.world) a += v[r];
+        p.SN[e] = a;
+    }
+}
+
 template <int NG>
-__device__ __noinline__ void step_update(const TcParams &p, int st, uint8_t *smem,
-                                         unsigned int &gb_target)
+__device__ __noinline__ void step_finish(const TcParams &p, int st, uint8_t *smem, int tid,
+                                         unsigned int &gb_target, uint64_t &tm)
 {
     const TcPlan &pl = p.plan;
     const int K = pl.K, C = pl.C, len = K * (C + 1);
-    const int tid = threadIdx.x, nthr = blockDim.x;
-    float *acc = reinterpret_cast<float *>(smem + pl.off_acc);
+    constexpr uint32_t nthr = (uint32_t)NG * 128u + 32u;
+    const bool leader = tid == 0;
     unsigned int *gsync = &p.ctl->grid_sync;
     const bool timing = blockIdx.x == 0 && tid == 0;
-    uint64_t tm = timing ? global_timer_ns() : 0;
     auto lap = [&](int slot) {
         if (timing) {
             const uint64_t now = global_timer_ns();
@@ -243,103 +593,68 @@ __device__ __noinline__ void step_update(const TcParams &p, int st, uint8_t *sme
             tm = now;
         }
     };
+    lap(0);  // tiles
 
-    // 1. groups -> this CTA's partial (group order), accumulators cleared for the next step
-    float *mine = p.partials + (size_t)blockIdx.x * len;
-    for (int i = tid; i < len; i += nthr) {
-        float v = acc[i];
-        acc[i] = 0.f;
-#pragma unroll
-        for (int gg = 1; gg < NG; ++gg) {
-            v += acc[gg * len + i];
-            acc[gg * len + i] = 0.f;
-        }
-        mine[i] = v;
-    }
-    gb_target += gridDim.x;
-    grid_barrier(gsync, gb_target);
-    lap(1);
-
-    // 2. every CTA folds its slice of the table over all partials, CTA order, fp64
-    double *fold_dst = p.world > 1 ? p.peer_buf[p.rank] + (size_t)(st & 1) * len : p.SN;
+    // 1. this CTA's part of the statistics: its NG group tables are added in group order, the
+    //    counts joined in, tables and counts cleared for the next step.
+    const bool tabg = pl.tab_global != 0;
+    if (tabg) __threadfence();  // this thread's red operations (fire-and-forget) are performed
+    bar_sync(kBarStep, nthr);   // every group is done with its last tile
+    const int ldp = part_pitch(C), plen = K * ldp;
+    int *cnt_s = reinterpret_cast<int *>(smem + pl.off_cnt);
     {
-        const int nparts = gridDim.x;
-        const int per = (len + nparts - 1) / nparts;
-        const int e0 = blockIdx.x * per;
-        const int e1 = min(len, e0 + per);
-        const int oct = tid >> 3, q = tid & 7;
-        const int rounds = (per + nthr / 8 - 1) / (nthr / 8);  // uniform trip count
-        for (int it = 0; it < rounds; ++it) {
-            const int e = e0 + it * (nthr / 8) + oct;
-            float v[kFoldMax];
+        float4 *grp = reinterpret_cast<float4 *>(p.partials + (size_t)blockIdx.x * NG * plen);
+        float4 *mine = reinterpret_cast<float4 *>(p.parts + (size_t)blockIdx.x * plen);
+        const float4 *acc4 = reinterpret_cast<const float4 *>(smem + pl.off_acc);
+        const int ldp4 = ldp >> 2, plen4 = plen >> 2, Cp4 = tab_pitch(C) >> 2;
+        const float4 zero4 = make_float4(0.f, 0.f, 0.f, 0.f);
+        for (int i = tid; i < plen4; i += (int)nthr) {
+            const int k = i / ldp4, q4 = i - k * ldp4, c4 = q4 * 4;
+            float4 v = zero4;
+            if (tabg) {
 #pragma unroll
-            for (int u = 0; u < kFoldMax; ++u) {
-                const int pp = q + 8 * u;
-                v[u] = (e < e1 && pp < nparts) ? __ldcg(p.partials + (size_t)pp * len + e) : 0.f;
-            }
-            double a = 0.0;
+                for (int gg = 0; gg < NG; ++gg) {
+                    const float4 u = __ldcg(grp + (size_t)gg * plen4 + i);
+                    __stcg(grp + (size_t)gg * plen4 + i, zero4);
+                    v.x += u.x, v.y += u.y, v.z += u.z, v.w += u.w;
+                }
+            } else if (q4 < Cp4) {
 #pragma unroll
-            for (int u = 0; u < kFoldMax; ++u) a += (double)v[u];
-            a += __shfl_xor_sync(0xffffffffu, a, 1);
-            a += __shfl_xor_sync(0xffffffffu, a, 2);
-            a += __shfl_xor_sync(0xffffffffu, a, 4);
-            if (e < e1 && q == 0) fold_dst[e] = a;
-        }
-    }
-    if (p.world > 1) {
-        // ---- cross-GPU sum over NVLink peer memory, fused into the step: every rank has folded
-        // its shard's table into its exchange buffer; after a flag handshake each CTA sums ITS
-        // slice over the ranks in rank order (so every rank computes bit-identical totals).
-        gb_target += gridDim.x;
-        grid_barrier(gsync, gb_target);  // this rank's buffer is complete
-        if (blockIdx.x == 0 && tid == 0) {
-            __threadfence_system();
-            const uint32_t val = p.flag_base + (uint32_t)st + 1u;
-            const size_t flag_off = (size_t)2 * len * sizeof(double);
-            for (int r = 0; r < p.world; ++r) {
-                if (r == p.rank) continue;
-                uint32_t *dst = reinterpret_cast<uint32_t *>(
-                                    reinterpret_cast<char *>(p.peer_buf[r]) + flag_off) + p.rank;
-                asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(dst), "r"(val) : "memory");
-            }
-            const uint32_t *mine_flags = reinterpret_cast<const uint32_t *>(
-                reinterpret_cast<const char *>(p.peer_buf[p.rank]) + flag_off);
-            for (int r = 0; r < p.world; ++r) {
-                if (r == p.rank) continue;
-                uint32_t seen, spins = 0;
-                do {
-                    asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(seen) : "l"(mine_flags + r) : "memory");
-                    if (seen - val < 0x80000000u) break;  // seen >= val (wrap-safe)
-                    __nanosleep(64);
-                    if (++spins > (1u << 26)) __trap();  // a peer died: fail instead of hanging
-                } while (true);
-            }
-        }
-        gb_target += gridDim.x;
-        grid_barrier(gsync, gb_target);  // all ranks' buffers are complete and visible
-        const int nparts = gridDim.x;
-        const int per = (len + nparts - 1) / nparts;
-        const int e0 = blockIdx.x * per;
-        const int e1 = min(len, e0 + per);
-        for (int e = e0 + tid; e < e1; e += nthr) {
-            // all ranks' values first (up to 8 NVLink round trips in flight together instead of one
-            // after the other), then the sum in rank order
-            double v[8];
-#pragma unroll
-            for (int r = 0; r < 8; ++r) {
-                v[r] = 0.0;
-                if (r < p.world) {
-                    const double *src = p.peer_buf[r] + (size_t)(st & 1) * len + e;
-                    asm volatile("ld.volatile.global.f64 %0, [%1];" : "=d"(v[r]) : "l"(src) : "memory");
+                for (int gg = 0; gg < NG; ++gg) {
+                    float4 *cell = const_cast<float4 *>(acc4) + ((size_t)gg * K + k) * Cp4 + q4;
+                    const float4 u = *cell;
+                    *cell = zero4;
+                    v.x += u.x, v.y += u.y, v.z += u.z, v.w += u.w;
                 }
             }
-            double a = 0.0;
+            if (c4 <= C && C < c4 + 4) {  // the chunk that holds the count column
+                int n = 0;
 #pragma unroll
-            for (int r = 0; r < 8; ++r)
-                if (r < p.world) a += v[r];
-            p.SN[e] = a;
+                for (int gg = 0; gg < NG; ++gg) {
+                    n += cnt_s[gg * K + k];
+                    cnt_s[gg * K + k] = 0;
+                }
+                (&v.x)[C - c4] = (float)n;
+            }
+            __stcg(mine + i, v);
         }
     }
+    gb_target += gridDim.x;
+    grid_barrier(gsync, gb_target, nthr, leader);
+    lap(1);
+
+    // 2. fold this CTA's slice
+    const int nparts = (int)gridDim.x;
+    const int per = (len + (int)gridDim.x - 1) / (int)gridDim.x;
+    const int e0 = min(len, (int)blockIdx.x * per), e1 = min(len, e0 + per);
+    double *s_slice = reinterpret_cast<double *>(smem + pl.off_pairs);  // pair lists are idle
+    const bool direct = p.world <= 1;
+    fold_slice_sum(p, nparts, len, e0, e1, per, tid, (int)nthr, direct ? p.SN + e0 : s_slice);
+    if (!direct) {
+        bar_sync(kBarStep, nthr);
+        exchange_slice(p, st, len, e0, e1, tid, (int)nthr, s_slice);
+    }
+    if (!p.apply) return;
     if (blockIdx.x == 0 && tid == 0) {
         // slot the update below publishes the next step's norms into
         p.ctl->pp_wmax_bits[(st + 1) & 1] = 0;
@@ -347,10 +662,10 @@ __device__ __noinline__ void step_update(const TcParams &p, int st, uint8_t *sme
     }
     lap(2);
     gb_target += gridDim.x;
-    grid_barrier(gsync, gb_target);
+    grid_barrier(gsync, gb_target, nthr, leader);
     lap(3);
 
-    // 3. batch update of node k by CTA k (k < K); schedule of step t = t0 + st of T
+    // 3. batch update; schedule of step t = t0 + st of T
     {
         const double frac = (double)(p.t0 + st) / (double)p.T;
         const double r = p.r0 - (p.r0 - p.r1) * frac;
@@ -358,56 +673,19 @@ __device__ __noinline__ void step_update(const TcParams &p, int st, uint8_t *sme
         const double sigma = 0.5 * r_eff;
         const double inv2s2 = 1.0 / (2.0 * sigma * sigma);
         const double alpha = p.a0 - (p.a0 - p.a1) * frac;
-        // the folded table, staged once per CTA in the (idle, already cleared) accumulator area
-        double *s_sn = reinterpret_cast<double *>(acc);
-        if ((int)blockIdx.x < K)
-            for (int i = tid; i < len; i += nthr) s_sn[i] = __ldcg(p.SN + i);
-        __syncthreads();
-        double *s_h = reinterpret_cast<double *>(smem + pl.off_pairs);  // [K], pair lists are idle
-        double *s_cnt = s_h + K;                                        // [K]
-        double *s_red = s_cnt + K;                                      // [32] block reduction
-        int *s_flag = reinterpret_cast<int *>(s_red + 32);
-        const int ydim = p.ydim;
-        for (int k = blockIdx.x; k < K; k += gridDim.x) {
-            const int kx = k / ydim, ky = k % ydim;
-            for (int b = tid; b < K; b += nthr) {
-                const int dx = abs(kx - b / ydim), dy = abs(ky - b % ydim);
-                const double d = (double)(dx > dy ? dx : dy);
-                const double cnt = s_sn[(size_t)b * (C + 1) + C];
-                s_cnt[b] = cnt;
-                s_h[b] = cnt == 0.0 ? 0.0 : exp(-d * d * inv2s2);
-            }
-            if (tid == 0) *s_flag = 0;
-            __syncthreads();
-            double den = 0.0;
-            for (int b = 0; b < K; ++b) den += s_h[b] * s_cnt[b];
-            const double beta = den > 0.0 ? 1.0 - pow(1.0 - alpha, den) : 0.0;
-            double nrm2 = 0.0;
-            bool neg = false;
-            char *img = reinterpret_cast<char *>(p.wimg_rw);
-            for (int c = tid; c < C; c += nthr) {
-                double w = p.W64[(size_t)k * C + c];
-                if (den > 0.0) {
-                    double num = 0.0;
-                    for (int b = 0; b < K; ++b) num += s_h[b] * s_sn[(size_t)b * (C + 1) + c];
-                    w += beta * (num / den - w);
-                    p.W64[(size_t)k * C + c] = w;
-                }
-                const float wf = (float)w;
-                p.W32[(size_t)k * C + c] = wf;
+        char *img = reinterpret_cast<char *>(p.wimg_rw);
+        int *wmax_slot = &p.ctl->pp_wmax_bits[(st + 1) & 1];
+        int *neg_slot = &p.ctl->pp_w_has_negative[(st + 1) & 1];
+        som_update_nodes(
+            p.SN, p.W64, p.W32, K, C, p.ydim, inv2s2, alpha, (int)blockIdx.x, (int)gridDim.x, tid,
+            (int)nthr, reinterpret_cast<double *>(smem + pl.off_pairs),
+            [&] { bar_sync(kBarStep, nthr); },
+            [&](int k, int c, float wf) {
                 *reinterpret_cast<float *>(img + img_offset(pl.Ntot, k, c)) = -2.0f * wf;
-                nrm2 += (double)wf * (double)wf;
-                if (__float_as_int(wf) < 0) neg = true;
-            }
-            // block reduction of ||w_k||^2 (only the first C threads contribute)
-            for (int o = 16; o > 0; o >>= 1) nrm2 += __shfl_xor_sync(0xffffffffu, nrm2, o);
-            if (neg) atomicOr(s_flag, 1);
-            if ((tid & 31) == 0 && (tid >> 5) < 32) s_red[tid >> 5] = nrm2;
-            __syncthreads();
-            if (tid == 0) {
-                double tot = 0.0;
-                for (int w = 0; w < (nthr + 31) / 32 && w < 32; ++w) tot += s_red[w];
-                float bias = (float)tot;
+            },
+            [&](int k, int lane, double nrm2, bool neg) {
+                if (lane != 0) return;
+                float bias = (float)nrm2;
                 if (!(bias <= FLT_MAX)) bias = FLT_MAX;
                 const float h = __uint_as_float(__float_as_uint(bias) & 0xFFFFE000u);
                 const float r1 = bias - h;
@@ -417,151 +695,25 @@ __device__ __noinline__ void step_update(const TcParams &p, int st, uint8_t *sme
                 bb[0] = h;
                 bb[1] = m;
                 bb[2] = l;
-                float nr = (float)sqrt(tot) * 1.0000005f;
+                float nr = (float)sqrt(nrm2) * 1.0000005f;
                 if (!(nr <= FLT_MAX)) nr = FLT_MAX;
-                atomicMax(&p.ctl->pp_wmax_bits[(st + 1) & 1], __float_as_int(nr));
-                if (*s_flag) atomicOr(&p.ctl->pp_w_has_negative[(st + 1) & 1], 1);
-            }
-            __syncthreads();
-        }
+                atomicMax(wmax_slot, __float_as_int(nr));
+                if (neg) atomicOr(neg_slot, 1);
+            });
     }
-    // the staged table sat in the accumulator area: clear it again for the next step
-    if ((int)blockIdx.x < K)
-        for (int i = tid; i < (len * 2 + 1); i += nthr)
-            if (i < NG * len) acc[i] = 0.f;
     lap(4);
     gb_target += gridDim.x;
-    grid_barrier(gsync, gb_target);
+    grid_barrier(gsync, gb_target, nthr, leader);
     lap(5);
-}
-
-// ------------------------------------------------------------------------------------------------
-// train mode: add one tile's rows to the epilogue group's private K x (C+1) table (sums + counts).
-// Called by the 128 threads of group g once the tile's labels are known (L = label bin of this
-// thread's row, K = "skip": padding and unassignable rows).  Deterministic, no atomics:
-//   1. stable counting sort of the 128 rows by label: rank inside the warp from match.any, one
-//      histogram byte per (warp, label), every warp scans the bins itself (32 lanes x nbl bins);
-//   2. warp w walks sorted positions [32w, 32w+32) with lanes = channels: the rows of a node are
-//      contiguous, so a node's sum is a register accumulation over independent shared-memory loads
-//      (the walk that used to be a 128-long chain of dependent read-modify-writes on the table);
-//      each finished segment is one read-modify-write on cells no other warp touches -- except the
-//      warp's FIRST segment, whose node may continue from the previous warp's range: that one goes
-//      to a side buffer;
-//   3. after a group barrier the side buffers are added in warp order.
-// Sum order inside a tile: ascending row inside a warp range, warp ranges in order.
-// ------------------------------------------------------------------------------------------------
-static __device__ __noinline__ void tile_accumulate_sorted(uint8_t *smem, const uint8_t *xs,
-                                                           uint32_t off_acc, uint32_t off_sort, int K,
-                                                           int C, int nblkX, int g, int quad,
-                                                           int lane, int L)
-{
-    const SortLayout sl = sort_layout(C, K);
-    uint8_t *base = smem + off_sort;
-    uint32_t *hist32 = reinterpret_cast<uint32_t *>(base);
-    uint8_t *wbase = base + sl.off_wbase + (uint32_t)quad * sl.bins;
-    uint8_t *order = base + sl.off_order;
-    uint16_t *slab = reinterpret_cast<uint16_t *>(base + sl.off_slab);
-    float *side = reinterpret_cast<float *>(base + sl.off_side);
-    int *side_lab = reinterpret_cast<int *>(base + sl.off_sidelab);
-    const int acc_ld = C + 1;
-    float *tab = reinterpret_cast<float *>(smem + off_acc) + (size_t)g * K * acc_ld;
-    const uint32_t bar = 1u + (uint32_t)g;
-
-    // 1a. rows of this warp with my label; the lowest such lane publishes their count
-    const unsigned peers = __match_any_sync(0xffffffffu, L);
-    const int rk = __popc(peers & ((1u << lane) - 1u));
-    if (rk == 0) base[4 * L + quad] = (uint8_t)__popc(peers);
-    bar_sync(bar, 128);
-    // 1b. every warp scans all bins: lane l owns bins [l * nbl, (l + 1) * nbl)
-    {
-        const uint32_t *hp = hist32 + (uint32_t)lane * sl.nbl;
-        uint32_t run = 0;
-        for (uint32_t i = 0; i < sl.nbl; ++i) run += __dp4a(hp[i], 0x01010101u, 0u);
-        uint32_t inc = run;
-#pragma unroll
-        for (int o = 1; o < 32; o <<= 1) {
-            const uint32_t t = __shfl_up_sync(0xffffffffu, inc, o);
-            if (lane >= o) inc += t;
-        }
-        uint32_t pos0 = inc - run;
-        const uint32_t below = 0x01010101u & ((1u << (8 * quad)) - 1u);  // warps before this one
-        uint8_t *wp = wbase + (uint32_t)lane * sl.nbl;
-        for (uint32_t i = 0; i < sl.nbl; ++i) {
-            const uint32_t w = hp[i];
-            wp[i] = (uint8_t)(pos0 + __dp4a(w, below, 0u));
-            pos0 += __dp4a(w, 0x01010101u, 0u);
-        }
+#ifdef PIXIE_PROFILE
+    if ((p.dbg_flags & 4) && timing) {
+        const unsigned long long *c = p.ctl->tile_cyc;
+        printf("step %2d tiles %llu | cyc: waitX %llu norm %llu passes %llu resolve %llu fix %llu accwork %llu accwait %llu | ns: tiles %llu b1 %llu fold %llu b2 %llu upd %llu b3 %llu\n",
+               st, c[6], c[0], c[1], c[2], c[3], c[4], c[5], c[7], p.ctl->phase_ns[0],
+               p.ctl->phase_ns[1], p.ctl->phase_ns[2], p.ctl->phase_ns[3], p.ctl->phase_ns[4],
+               p.ctl->phase_ns[5]);
     }
-    __syncwarp();
-    {
-        const int pos = (int)wbase[L] + rk;
-        order[pos] = (uint8_t)(quad * 32 + lane);
-        slab[pos] = (uint16_t)L;
-    }
-    bar_sync(bar, 128);
-    if (rk == 0) base[4 * L + quad] = 0;  // histograms are zero again for the next tile
-
-    // 2. segment walk
-    const int my_row = order[quad * 32 + lane];
-    const int my_L = slab[quad * 32 + lane];
-    if (lane == 0) side_lab[quad] = -1;
-    for (int cb = 0; cb < nblkX; ++cb) {
-        const int ch = cb * 32 + lane;
-        const uint8_t *xb = xs + (uint32_t)cb * 16384u + (uint32_t)(lane & 3) * 4u;
-        const uint32_t chunk = (uint32_t)lane >> 2;
-        float a = 0.f;
-        int curL = __shfl_sync(0xffffffffu, my_L, 0), seg_len = 0;
-        bool first = true;
-        auto flush = [&]() {
-            if (curL < K) {
-                if (first) {
-                    if (ch < C) side[quad * acc_ld + ch] = a;
-                    if (cb == 0 && lane == 0) {
-                        side[quad * acc_ld + C] = (float)seg_len;
-                        side_lab[quad] = curL;
-                    }
-                } else {
-                    if (ch < C) tab[curL * acc_ld + ch] += a;
-                    if (cb == 0 && lane == 0) tab[curL * acc_ld + C] += (float)seg_len;
-                }
-            }
-        };
-#pragma unroll 1
-        for (int i0 = 0; i0 < 32; i0 += 16) {
-            float v[16];
-#pragma unroll
-            for (int u = 0; u < 16; ++u) {
-                const uint32_t r = (uint32_t)__shfl_sync(0xffffffffu, my_row, i0 + u);
-                v[u] = *reinterpret_cast<const float *>(xb + r * 128u + ((chunk ^ (r & 7u)) << 4));
-            }
-#pragma unroll
-            for (int u = 0; u < 16; ++u) {
-                const int Lu = __shfl_sync(0xffffffffu, my_L, i0 + u);
-                if (Lu != curL) {  // warp-uniform
-                    flush();
-                    first = false;
-                    curL = Lu;
-                    a = 0.f;
-                    seg_len = 0;
-                }
-                if (Lu < K) {
-                    a += v[u];
-                    ++seg_len;
-                }
-            }
-        }
-        if (seg_len > 0) flush();
-    }
-    bar_sync(bar, 128);
-    // 3. side buffers, warp order; thread t of the group owns column t of the table
-    const int col = quad * 32 + lane;
-    if (col <= C) {
-#pragma unroll
-        for (int w = 0; w < 4; ++w) {
-            const int sL = side_lab[w];
-            if (sL >= 0) tab[sL * acc_ld + col] += side[w * acc_ld + col];
-        }
-    }
+#endif
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -625,11 +777,14 @@ bmu_tc_kernel(const __grid_constant__ CUtensorMap tmX, const TcParams p)
     }
     for (int i = threadIdx.x; i < 1024; i += blockDim.x) reinterpret_cast<float *>(ones)[i] = 1.0f;
     if constexpr (ACC) {
-        float *a = reinterpret_cast<float *>(smem + pl.off_acc);
-        for (int i = threadIdx.x; i < NG * pl.K * (pl.C + 1); i += blockDim.x) a[i] = 0.f;
-        // the sort scratch keeps its histograms zero between tiles
-        uint32_t *sc = reinterpret_cast<uint32_t *>(smem + pl.off_lab);
-        for (uint32_t i = threadIdx.x; i < (uint32_t)NG * pl.sort_stride / 4u; i += blockDim.x) sc[i] = 0u;
+        // shared-memory tables and the counts start at zero (global tables are cleared by the host
+        // before the launch and by their owner after every step)
+        if (!pl.tab_global) {
+            float *a = reinterpret_cast<float *>(smem + pl.off_acc);
+            for (int i = threadIdx.x; i < NG * pl.K * tab_pitch(pl.C); i += blockDim.x) a[i] = 0.f;
+        }
+        int *cz = reinterpret_cast<int *>(smem + pl.off_cnt);
+        for (int i = threadIdx.x; i < NG * pl.K; i += blockDim.x) cz[i] = 0;
     }
     fence_proxy_async();  // the ones tile is read by the tensor core (async proxy)
     tc_fence_before();
@@ -642,46 +797,70 @@ bmu_tc_kernel(const __grid_constant__ CUtensorMap tmX, const TcParams p)
     // across ALL steps; it fixes the pipeline slot of a tile: X stage seq % nstage, epilogue group
     // seq % NG, accumulator use seq / NG -- so barrier phases simply keep running across steps.
     uint32_t base_seq = 0;
-    unsigned int gb_target = 0;
+    unsigned int gb_target = 0;  // grid-barrier instances passed so far x gridDim.x
     uint32_t st_flag = 0, st_pairs = 0, st_fp64 = 0, st_fix = 0;  // per-thread statistics
-    uint64_t step_t0 = (ACC && blockIdx.x == 0 && threadIdx.x == 0) ? global_timer_ns() : 0;  // grid-barrier instances passed so far x gridDim.x
-    for (int st = 0; st < nsteps; ++st) {
-    const StepTiles stp = ACC ? step_tiles(p, st) : StepTiles{p.tile_first, p.tile_stride, p.ntiles};
-    const int64_t ntiles = stp.count;
-    const uint32_t cnt =
-        (int64_t)blockIdx.x < ntiles ? (uint32_t)((ntiles - blockIdx.x + gridDim.x - 1) / gridDim.x) : 0u;
+    uint64_t lap_t = (ACC && blockIdx.x == 0 && threadIdx.x == 0) ? global_timer_ns() : 0;
+    PIXIE_PROF_DECL();
+    // thread index among the non-producer threads (epilogue warps, then the MMA warp)
+    const int tid_np = warp < NEPI ? (int)threadIdx.x : (int)threadIdx.x - 32;
 
-    if (warp == NEPI) {
-        // ============================================================ TMA producer
-        // The whole warp walks the loop (warp-uniform control flow); one elected lane issues.
-        {
-            if (elect_one()) {
-                // codebook image: linear bulk copies (image is pre-swizzled in global memory); in
-                // whole-pass mode it was rewritten by other CTAs through the generic proxy
-                asm volatile("fence.proxy.async;" ::: "memory");
-                mbar_arrive_expect_tx(bar_w, pl.wimg_bytes);
-                for (uint32_t off = 0; off < pl.wimg_bytes; off += 16384u) {
-                    const uint32_t sz = min(16384u, pl.wimg_bytes - off);
-                    bulk_load(sbase + off, reinterpret_cast<const uint8_t *>(p.wimg) + off, sz, bar_w);
-                }
-            }
-            __syncwarp();
-            uint32_t s = base_seq % (uint32_t)nstage;          // one division per step, then
-            uint32_t ph = (base_seq / (uint32_t)nstage) & 1u;  // incremental
-            for (uint32_t it = 0; it < cnt; ++it, ph ^= (++s == (uint32_t)nstage), s = s == (uint32_t)nstage ? 0u : s) {
-                mbar_wait(bar_empty + 8u * s, ph ^ 1u);
-                const int64_t j = (int64_t)blockIdx.x + (int64_t)it * gridDim.x;
-                const int64_t tile = stp.first + j * stp.stride;
-                const int32_t row0 = (int32_t)(tile * kTile);
-                if (elect_one()) {
-                    mbar_arrive_expect_tx(bar_full + 8u * s, pl.stage_bytes);
-                    for (int b = 0; b < pl.nblkX; ++b)
-                        tma_load_2d(sbase + pl.off_x + s * pl.stage_bytes + (uint32_t)b * 16384u,
-                                    &tmX, bar_full + 8u * s, b * 32, row0, kEvictFirst);
-                }
-                __syncwarp();
+    // codebook image -> shared memory: linear bulk copies (the image is pre-swizzled in global
+    // memory); in whole-pass mode it was rewritten by other CTAs through the generic proxy
+    auto load_image = [&]() {
+        if (elect_one()) {
+            asm volatile("fence.proxy.async;" ::: "memory");
+            mbar_arrive_expect_tx(bar_w, pl.wimg_bytes);
+            for (uint32_t off = 0; off < pl.wimg_bytes; off += 16384u) {
+                const uint32_t sz = min(16384u, pl.wimg_bytes - off);
+                bulk_load(sbase + off, reinterpret_cast<const uint8_t *>(p.wimg) + off, sz, bar_w);
             }
         }
+        __syncwarp();
+    };
+    // X tiles of one step -> stages.  The whole warp walks the loop (warp-uniform control flow);
+    // one elected lane issues.
+    auto produce_step = [&](const StepTiles &stp, uint32_t cnt, uint32_t seq0, int st) {
+        uint32_t s = seq0 % (uint32_t)nstage;          // one division per step, then
+        uint32_t ph = (seq0 / (uint32_t)nstage) & 1u;  // incremental
+        for (uint32_t it = 0; it < cnt; ++it, ph ^= (++s == (uint32_t)nstage), s = s == (uint32_t)nstage ? 0u : s) {
+            mbar_wait(bar_empty + 8u * s, ph ^ 1u);
+            const int64_t j = (int64_t)blockIdx.x + (int64_t)it * gridDim.x;
+            const int64_t tile = stp.first + j * stp.stride;
+            const int32_t row0 = (int32_t)(tile * kTile);
+            if (elect_one()) {
+                mbar_arrive_expect_tx(bar_full + 8u * s, pl.stage_bytes);
+                for (int b = 0; b < pl.nblkX; ++b)
+                    tma_load_2d(sbase + pl.off_x + s * pl.stage_bytes + (uint32_t)b * 16384u,
+                                &tmX, bar_full + 8u * s, b * 32, row0, kEvictFirst);
+            }
+            __syncwarp();
+            PIXIE_TRACE(0, seq0 + it);
+        }
+    };
+    auto tiles_of = [&](const StepTiles &stp) {
+        return (int64_t)blockIdx.x < stp.count
+                   ? (uint32_t)((stp.count - blockIdx.x + gridDim.x - 1) / gridDim.x) : 0u;
+    };
+
+    if (ACC && warp == NEPI) {
+        // ============================================================ TMA producer, train mode
+        // Runs through ALL steps on its own: X does not depend on the codebook, so the next step's
+        // first tiles are already in flight while the other warps finish the current step.
+        for (int st = 0; st < nsteps; ++st) {
+            const StepTiles stp = step_tiles(p, st);
+            const uint32_t cnt = tiles_of(stp);
+            produce_step(stp, cnt, base_seq, st);
+            base_seq += cnt;
+        }
+    } else {
+    for (int st = 0; st < nsteps; ++st) {
+    const StepTiles stp = ACC ? step_tiles(p, st) : StepTiles{p.tile_first, p.tile_stride, p.ntiles};
+    const uint32_t cnt = tiles_of(stp);
+
+    if (warp == NEPI) {
+        // ============================================================ TMA producer (assignment)
+        load_image();
+        produce_step(stp, cnt, base_seq, st);
     } else if (warp == NEPI + 1) {
         // ============================================================ MMA issuer
         // The whole warp walks the loop and waits on the barriers; one elected lane (always the
@@ -691,12 +870,14 @@ bmu_tc_kernel(const __grid_constant__ CUtensorMap tmX, const TcParams p)
             const uint64_t desc_ones = umma_desc_nosw(sbase + pl.off_ones, 128u, 256u);
             // bias K-step: the no-swizzle block behind the image (8-row groups 256 bytes apart)
             const uint32_t wblk_bytes = (uint32_t)((NCH - 1) * NCHUNK + NMMA) * 128u;
+            if constexpr (ACC) load_image();  // this step's codebook (the producer warp is busy ahead)
             mbar_wait(bar_w, (uint32_t)st & 1u);
             uint32_t s = base_seq % (uint32_t)nstage;
             uint32_t ph = (base_seq / (uint32_t)nstage) & 1u;
             for (uint32_t it = 0; it < cnt; ++it, ph ^= (++s == (uint32_t)nstage), s = s == (uint32_t)nstage ? 0u : s) {
                 const uint32_t seq = base_seq + it;
                 mbar_wait(bar_full + 8u * s, ph);
+                PIXIE_TRACE(1, seq);
                 const uint32_t xs_addr = sbase + pl.off_x + s * pl.stage_bytes;
 #pragma unroll
                 for (int c = 0; c < NCH; ++c) {
@@ -720,6 +901,7 @@ bmu_tc_kernel(const __grid_constant__ CUtensorMap tmX, const TcParams p)
                     mma_commit(bar_tfull + 8u * buf);
                     }
                     __syncwarp();
+                    PIXIE_TRACE(2, seq);
                 }
             }
         }
@@ -765,7 +947,10 @@ bmu_tc_kernel(const __grid_constant__ CUtensorMap tmX, const TcParams p)
             const uint32_t use = seq / (uint32_t)NG;  // NG is a power of two: a shift
             const uint8_t *xs = xs0 + (uint32_t)s * pl.stage_bytes;
 
+            PIXIE_TICK(0);
             mbar_wait(bar_full + 8u * s, ph);  // X tile landed
+            PIXIE_TOCK(0);
+            PIXIE_TRACE(3, seq);
 
             // ---- per-row error bound of the tf32 scores.  ||x||^2 and the
             // sign test read whole 128-byte rows in physical order: channels past C are zero-filled
@@ -807,6 +992,7 @@ bmu_tc_kernel(const __grid_constant__ CUtensorMap tmX, const TcParams p)
             const float delta =
                 ((w_nonneg && (int32_t)sgn >= 0) ? 1.03125f * E : 2.0f * E) * p.delta_scale;
 
+            PIXIE_TOCK(1);
             float m_run = __int_as_float(0x7f800000);
             uint32_t mw[NS][NW];
 #pragma unroll
@@ -833,6 +1019,7 @@ bmu_tc_kernel(const __grid_constant__ CUtensorMap tmX, const TcParams p)
                 }
                 mbar_wait(bar_tfull + 8u * buf, bph);
                 tc_fence_after();
+                PIXIE_TRACE(4, seq);
 #pragma unroll
                 for (int sidx = 0; sidx < SPC; ++sidx) {
                     const int sl = c * SPC + sidx;
@@ -897,6 +1084,8 @@ bmu_tc_kernel(const __grid_constant__ CUtensorMap tmX, const TcParams p)
                 bar_sync(1u + (uint32_t)g, 128);
             }
 
+            PIXIE_TOCK(2);
+            PIXIE_TRACE(5, seq);
             // ---- resolve
             int nc = 0;
 #pragma unroll
@@ -1045,11 +1234,17 @@ bmu_tc_kernel(const __grid_constant__ CUtensorMap tmX, const TcParams p)
                 __syncwarp();  // pair buffers are reused by the next tile
             }
             if (label > pl.K) label = kLabelFixup;  // a padded codebook row can only win on garbage
+            PIXIE_TOCK(3);
             if constexpr (ACC) {
                 // Train mode resolves the rare rows the three stages could not settle right here
                 // (their sums must be in this step's table): the warp runs the reference loop for
                 // such a row cooperatively, lane l over nodes l, l+32, ...; the lexicographic
                 // (distance, index) minimum over lanes is the first minimum of the sequential loop.
+                // A row that only had too many candidates (a collapsed map early in training: more
+                // than kMaxCand nodes inside the window, or a full pair list) does not need all K
+                // nodes: its candidate masks are a proven superset of the minimum, so the lanes
+                // share out THOSE nodes (up to 64; node order = mask order) -- K / nc times less
+                // fp64 work per row.  Rows with non-finite scores take the full loop.
                 unsigned fixm = __ballot_sync(0xffffffffu, label == kLabelFixup && grow < p.n);
                 while (fixm) {
                     const int src = __ffs(fixm) - 1;
@@ -1057,11 +1252,45 @@ bmu_tc_kernel(const __grid_constant__ CUtensorMap tmX, const TcParams p)
                     const int frow = quad * 32 + src;
                     int minid = 0x7fffffff;
                     double mind = DBL_MAX;
-                    for (int k = lane; k < pl.K; k += 32) {
-                        const double d = pair_dist_f64(xs, ws, Ntot, pl.C, frow, k);
-                        if (d < mind) {
-                            mind = d;
-                            minid = k;
+                    const int nc_src = __shfl_sync(0xffffffffu, finite ? nc : 0, src);
+                    if (nc_src >= 2 && nc_src <= 64) {
+                        int myk0 = -1, myk1 = -1, rank = 0;
+#pragma unroll
+                        for (int a = 0; a < NS; ++a)
+#pragma unroll
+                            for (int w = 0; w < NW; ++w) {
+                                const int cw = (SL - 32 * w) < 32 ? (SL - 32 * w) : 32;
+                                const int base = a * SL + 32 * w + cw - 32;
+                                uint32_t m = __shfl_sync(0xffffffffu, mw[a][w], src);
+                                while (m) {  // warp-uniform
+                                    const int lz = __clz(m);
+                                    m &= ~(0x80000000u >> lz);
+                                    if ((rank & 31) == lane) {
+                                        if (rank < 32) myk0 = base + lz; else myk1 = base + lz;
+                                    }
+                                    ++rank;
+                                }
+                            }
+                        if (myk0 >= 0 && myk0 < pl.K) {
+                            mind = pair_dist_f64(xs, ws, Ntot, pl.C, frow, myk0);
+                            minid = myk0;
+                        }
+                        if (__any_sync(0xffffffffu, myk1 >= 0) && myk1 >= 0 && myk1 < pl.K) {
+                            const double d = pair_dist_f64(xs, ws, Ntot, pl.C, frow, myk1);
+                            if (d < mind) {  // myk1 > myk0: strict < keeps the lower index on ties
+                                mind = d;
+                                minid = myk1;
+                            }
+                        }
+                        if (!(mind == mind)) mind = DBL_MAX, minid = 0x7fffffff;
+                    }
+                    if (!__any_sync(0xffffffffu, minid != 0x7fffffff)) {
+                        for (int k = lane; k < pl.K; k += 32) {
+                            const double d = pair_dist_f64(xs, ws, Ntot, pl.C, frow, k);
+                            if (d < mind) {
+                                mind = d;
+                                minid = k;
+                            }
                         }
                     }
                     for (int o = 16; o > 0; o >>= 1) {
@@ -1094,12 +1323,28 @@ bmu_tc_kernel(const __grid_constant__ CUtensorMap tmX, const TcParams p)
                     *lab_ptr = 0;  // padding row of the last tile: never counted
                 }
             }
+            PIXIE_TOCK(4);
+            PIXIE_TRACE(6, seq);
             if constexpr (do_acc) {
-                // ---- fused per-node sums (deterministic, no atomics): see tile_accumulate_sorted
-                tile_accumulate_sorted(smem, xs, pl.off_acc, pl.off_lab + (uint32_t)g * pl.sort_stride,
-                                       pl.K, pl.C, pl.nblkX, g, quad, lane,
-                                       (grow < p.n && label > 0) ? label - 1 : pl.K);
+                // ---- fused per-node sums (deterministic, no atomics between warps)
+                float *tab_s = reinterpret_cast<float *>(smem + pl.off_acc) +
+                               (size_t)g * pl.K * tab_pitch(pl.C);
+                float *tab_g = pl.tab_global
+                                   ? p.partials + ((size_t)blockIdx.x * NG + (size_t)g) * pl.K *
+                                                      part_pitch(pl.C)
+                                   : nullptr;
+                publish_labels(smem, pl.off_lab + (uint32_t)g * 512u,
+                               reinterpret_cast<int *>(smem + pl.off_cnt) + g * pl.K, pl.K, g, quad,
+                               lane, (grow < p.n && label > 0) ? label - 1 : pl.K, use & 1u);
+                PIXIE_TOCK(7);
+                PIXIE_TRACE(7, seq);
+                tile_accumulate(p, smem, sbase + pl.off_x + (uint32_t)s * pl.stage_bytes,
+                                smem_u32(tab_s), tab_g, pl.off_lab + (uint32_t)g * 512u,
+                                smem_u32(pairs), quad, lane, use & 1u);
             }
+            PIXIE_TOCK(5);
+            PIXIE_TRACE(8, seq);
+            PIXIE_TILE_DONE();
             // all reads of this X stage by this warp are done
             __syncwarp();
             if (lane == 0) mbar_arrive(bar_empty + 8u * s);
@@ -1113,17 +1358,13 @@ bmu_tc_kernel(const __grid_constant__ CUtensorMap tmX, const TcParams p)
     // ================================================================ end of step st
     base_seq += cnt;
     if constexpr (ACC) {
-        if (p.apply) {
-            __syncthreads();
-            if (blockIdx.x == 0 && threadIdx.x == 0) {
-                const uint64_t now = global_timer_ns();
-                p.ctl->phase_ns[0] += now - step_t0;
-            }
-            step_update<NG>(p, st, smem, gb_target);
-            if (blockIdx.x == 0 && threadIdx.x == 0) step_t0 = global_timer_ns();
-        }
+        PIXIE_PROF_FLUSH();
+        PIXIE_TRACE(9, 0);
+        step_finish<NG>(p, st, smem, tid_np, gb_target, lap_t);
+        PIXIE_TRACE(10, 0);
     }
     }  // for st
+    }  // non-producer roles
 
     if (warp < NEPI) {
         if (p.stats) {
@@ -1149,68 +1390,6 @@ bmu_tc_kernel(const __grid_constant__ CUtensorMap tmX, const TcParams p)
     if (warp == NEPI + 1) {
         tc_fence_after();
         tmem_dealloc(tmem_base, (uint32_t)pl.tmem_cols);
-    }
-    if (ACC && !p.apply) {
-        // ---- fused sums, part 2: groups are combined in group order into this CTA's partial,
-        // then (grid barrier; every CTA is resident: grid <= SM count, one CTA per SM) each CTA
-        // folds its slice of the table over all partials in CTA order, in fp64.
-        const int len = pl.K * (pl.C + 1);
-        const float *a = reinterpret_cast<const float *>(smem + pl.off_acc);
-        float *mine = p.partials + (size_t)blockIdx.x * len;
-        for (int i = threadIdx.x; i < len; i += blockDim.x) {
-            float v = a[i];
-#pragma unroll
-            for (int gg = 1; gg < NG; ++gg) v += a[gg * len + i];
-            mine[i] = v;
-        }
-        unsigned int *sync = p.ctl->sums_sync;
-        __threadfence();
-        __syncthreads();
-        if (threadIdx.x == 0) {
-            atomicAdd(&sync[0], 1u);
-            unsigned spins = 0;
-            while (atomicAdd(&sync[0], 0u) < gridDim.x) {
-                __nanosleep(64);
-                if (++spins > (1u << 24)) __trap();
-            }
-        }
-        __syncthreads();
-        __threadfence();
-        {
-            const int nparts = gridDim.x;
-            const int per = (len + nparts - 1) / nparts;
-            const int e0 = blockIdx.x * per;
-            const int e1 = min(len, e0 + per);
-            const int nthr = blockDim.x;           // multiple of 32
-            const int oct = threadIdx.x >> 3, q = threadIdx.x & 7;
-            const int rounds = (per + nthr / 8 - 1) / (nthr / 8);  // uniform trip count
-            for (int it = 0; it < rounds; ++it) {
-                const int e = e0 + it * (nthr / 8) + oct;
-                // all loads of this thread first (independent, in flight together), then the sum
-                // in ascending CTA order
-                float v[kFoldMax];
-#pragma unroll
-                for (int u = 0; u < kFoldMax; ++u) {
-                    const int pp = q + 8 * u;
-                    v[u] = (e < e1 && pp < nparts) ? __ldcg(p.partials + (size_t)pp * len + e) : 0.f;
-                }
-                double acc = 0.0;
-#pragma unroll
-                for (int u = 0; u < kFoldMax; ++u) acc += (double)v[u];
-                acc += __shfl_xor_sync(0xffffffffu, acc, 1);
-                acc += __shfl_xor_sync(0xffffffffu, acc, 2);
-                acc += __shfl_xor_sync(0xffffffffu, acc, 4);
-                if (e < e1 && q == 0) p.SN[e] = acc;
-            }
-        }
-        __syncthreads();
-        if (threadIdx.x == 0) {
-            if (atomicAdd(&sync[1], 1u) == gridDim.x - 1) {
-                sync[0] = 0u;
-                sync[1] = 0u;
-                __threadfence();
-            }
-        }
     }
 }
 

@@ -13,6 +13,10 @@
 using namespace pixie;
 
 namespace pixie {
+#ifdef PIXIE_PROFILE
+static unsigned long long *g_trace = nullptr;   // device: 2 x 2^15 words
+static unsigned int *g_trace_count = nullptr;   // device
+#endif
 static std::atomic<unsigned long long> g_launches{0};
 void count_launch(int n) { g_launches.fetch_add((unsigned long long)n, std::memory_order_relaxed); }
 }  // namespace pixie
@@ -115,7 +119,8 @@ float delta_scale_from_env()
 struct Workspace {
     float *wimg;
     CodebookAux *aux;
-    float *partials;
+    float *partials;  // group tables of the fused sums: [kSumParts x NG <= 4][K][part_pitch(C)]
+    float *parts;     // CTA parts: [kSumParts][K][part_pitch(C)]
     int32_t *labels_scratch;
     size_t total;
 };
@@ -129,13 +134,26 @@ Workspace carve(void *base, int64_t n_visit, int C, int K)
     off += align_up(wimg_max, 1024);
     w.aux = reinterpret_cast<CodebookAux *>((char *)base + off);
     off += 256;
+    const size_t table = (size_t)K * part_pitch(C) * sizeof(float);
     w.partials = reinterpret_cast<float *>((char *)base + off);
-    off += align_up((size_t)kSumParts * K * (C + 1) * sizeof(float), 256);
+    off += align_up((size_t)kSumParts * 4 * table, 256);
+    w.parts = reinterpret_cast<float *>((char *)base + off);
+    off += align_up((size_t)kSumParts * table, 256);
     w.labels_scratch = reinterpret_cast<int32_t *>((char *)base + off);
     const int64_t tiles = (n_visit + kTile - 1) / kTile + 1;
     off += align_up((size_t)tiles * kTile * sizeof(int32_t), 256);
     w.total = off;
     return w;
+}
+
+// the group tables are accumulated into in place: they start a launch at zero (every step leaves
+// them so, but the workspace may be new or may have served another shape)
+cudaError_t clear_group_tables(const TcPlan &plan, const Workspace &ws, cudaStream_t stream)
+{
+    if (!plan.tab_global) return cudaSuccess;
+    return cudaMemsetAsync(ws.partials, 0,
+                           (size_t)kSumParts * plan.NG * plan.K * part_pitch(plan.C) * sizeof(float),
+                           stream);
 }
 
 // BMU over the tiles {tile_first + j * tile_stride}, j < ntiles.  When SN != null the per-node sums
@@ -182,9 +200,12 @@ int bmu_tiles(const float *X, int64_t n, int C, int64_t ldX, const float *W, int
         p.stats = stats;
         p.ctl = ws.aux;
         p.partials = fused ? ws.partials : nullptr;
+        p.parts = fused ? ws.parts : nullptr;
         p.SN = fused ? SN : nullptr;
         p.delta_scale = delta_scale_from_env();
+        p.dbg_flags = getenv("PIXIE_DBG_FLAGS") ? atoi(getenv("PIXIE_DBG_FLAGS")) : 0;
         p.plan = plan;
+        if (fused) PX_CUDA(clear_group_tables(plan, ws, stream));
         PX_CUDA(launch_bmu_tc(tm, p, sum_parts(), stream));
         // rows the tensor-core kernel could not settle (NaN/Inf rows, degenerate codebooks): exact
         // kernel; returns immediately when the counter is zero.  In fused mode it also adds those
@@ -231,6 +252,23 @@ const char *pixie_error_string(int code)
 unsigned long long pixie_kernel_launches(void)
 {
     return pixie::g_launches.load(std::memory_order_relaxed);
+}
+
+/* diagnostic builds (make prof): copies the event trace of the last launches to the host and
+ * resets it; returns the number of events (0 in production builds) */
+int pixie_debug_trace(unsigned long long *out_host, int max_events)
+{
+#ifdef PIXIE_PROFILE
+    // 32 warps x 1024 slots of two words; unused slots are zero
+    if (!pixie::g_trace || max_events < (1 << 15)) return 0;
+    if (cudaMemcpy(out_host, pixie::g_trace, (size_t)(1u << 15) * 16, cudaMemcpyDeviceToHost) != cudaSuccess)
+        return -1;
+    return 1 << 15;
+#else
+    (void)out_host;
+    (void)max_events;
+    return 0;
+#endif
 }
 
 int pixie_device_count(void)
@@ -468,13 +506,24 @@ static int launch_whole_pass(const float *X, int64_t n, int32_t C, int64_t ldX, 
     const int K = xdim * ydim;
     TcPlan plan = make_tc_plan(C, K, true);
     const bool aligned = ((reinterpret_cast<uintptr_t>(X) & 15u) == 0) && (ldX % 4 == 0) &&
-                         n < ((int64_t)1 << 31) - kTile && n > 0;
+                         n < ((int64_t)1 << 31) - kTile;
     Workspace ws = carve(workspace, 0, C, K);
     if (!workspace || ws_bytes < ws.total) return PIXIE_ERR_WORKSPACE;
     CUtensorMap tm;
-    if (!plan.ok || !aligned || (flags & PIXIE_FLAG_FORCE_EXACT) || world < 1 || world > 8 ||
-        !make_x_tensor_map(&tm, X, n, C, ldX))
+    if (!plan.ok || !aligned || (flags & PIXIE_FLAG_FORCE_EXACT) || world < 1 || world > 8)
         return PIXIE_ERR_UNSUPPORTED;
+    // a rank without rows (fewer tiles than ranks) still runs the kernel -- it folds, exchanges and
+    // updates like the others; its tensor map points at one tile of scratch that is never loaded
+    const bool empty = n == 0;
+    if (!make_x_tensor_map(&tm, empty ? ws.wimg : X, empty ? kTile : n, C,
+                           empty ? (int64_t)(C + 3) / 4 * 4 : ldX))
+        return PIXIE_ERR_UNSUPPORTED;
+    if (world > 1) {
+        const int len = K * (C + 1);
+        const int grid = sum_parts();
+        if ((size_t)((len + grid - 1) / grid) * sizeof(double) > plan.pairs_bytes)
+            return PIXIE_ERR_UNSUPPORTED;
+    }
     const int64_t T = (int64_t)rlen * batches_per_pass;
     PX_CUDA(cudaMemsetAsync(ws.aux, 0, sizeof(CodebookAux), st));
     PX_CUDA(cudaMemsetAsync(SN, 0, sizeof(double) * (size_t)K * (C + 1), st));
@@ -493,6 +542,7 @@ static int launch_whole_pass(const float *X, int64_t n, int32_t C, int64_t ldX, 
     p.stats = nullptr;
     p.ctl = ws.aux;
     p.partials = ws.partials;
+    p.parts = ws.parts;
     p.SN = SN;
     p.nsteps = (int)T;
     p.apply = 1;
@@ -512,9 +562,22 @@ static int launch_whole_pass(const float *X, int64_t n, int32_t C, int64_t ldX, 
     p.rank = rank;
     p.flag_base = flag_base;
     p.delta_scale = delta_scale_from_env();
+    p.dbg_flags = getenv("PIXIE_DBG_FLAGS") ? atoi(getenv("PIXIE_DBG_FLAGS")) : 0;
+    p.dbg_step0 = getenv("PIXIE_TRACE_STEP") ? atoi(getenv("PIXIE_TRACE_STEP")) : 1 << 30;
+#ifdef PIXIE_PROFILE
+    if (!pixie::g_trace) {
+        cudaMalloc(&pixie::g_trace, (size_t)2 * (1u << 15) * 8);
+        cudaMalloc(&pixie::g_trace_count, 4);
+        cudaMemset(pixie::g_trace_count, 0, 4);
+    }
+    cudaMemsetAsync(pixie::g_trace, 0, (size_t)2 * (1u << 15) * 8, st);
+    p.trace = pixie::g_trace;
+    p.trace_count = pixie::g_trace_count;
+#endif
     for (int r = 0; r < 8; ++r)
         p.peer_buf[r] = (world > 1 && r < world) ? reinterpret_cast<double *>(peer_bufs[r]) : nullptr;
     p.plan = plan;
+    PX_CUDA(clear_group_tables(plan, ws, st));
     PX_CUDA(launch_bmu_tc(tm, p, sum_parts(), st));
     return PIXIE_OK;
 }
@@ -666,7 +729,18 @@ int pixie_som_train_f32(const float *X, int64_t n, int32_t C, int64_t ldX, doubl
 size_t pixie_peer_buffer_bytes(int32_t C, int32_t K)
 {
     if (C < 1 || K < 1) return 0;
-    return (size_t)2 * K * (C + 1) * sizeof(double) + 8 * sizeof(uint32_t) + 224;
+    // vals double [2][8][K (C+1)] + flags uint32 [2][8][kSumParts]  (exchange_slice, bmu_tc_kernel.cuh)
+    return (size_t)2 * 8 * K * (C + 1) * sizeof(double) + (size_t)2 * 8 * kSumParts * sizeof(uint32_t) +
+           256;
+}
+
+int pixie_som_train_peers_supported(int32_t C, int32_t K, int64_t ldX, int32_t x_aligned16)
+{
+    if (C < 1 || K < 1 || ldX < C || (ldX % 4) != 0 || !x_aligned16) return 0;
+    const TcPlan plan = make_tc_plan(C, K, true);
+    if (!plan.ok) return 0;
+    const int len = K * (C + 1), grid = sum_parts();
+    return (size_t)((len + grid - 1) / grid) * sizeof(double) <= plan.pairs_bytes ? 1 : 0;
 }
 
 int pixie_som_train_peers_f32(const float *X, int64_t n, int32_t C, int64_t ldX, double *W64,

@@ -14,7 +14,8 @@ constexpr int kTile = PIXIE_TILE;  // rows per tile == UMMA M == TMEM lanes
 constexpr int kLabelFixup = -1;    // sentinel: row must be resolved by the exact fix-up kernel
 constexpr int kMaxCand = 15;       // candidate nodes kept per row before giving up to the fix-up
 constexpr int kWarpPairCap = 256;  // (row, node) pairs re-evaluated per tile by one epilogue warp
-constexpr int kWarpPairCapAcc = 256;  // ... in train mode, where shared memory also holds the sums
+constexpr int kWarpPairCapAcc = 128;  // ... in train mode, where shared memory also holds the sums
+                                      // (the buffer doubles as the accumulate list: 128 x 8 bytes)
 constexpr int kMaxStages = 8;
 constexpr int kBarBlock = 256;     // bytes of shared memory reserved for mbarriers
 
@@ -33,7 +34,12 @@ struct CodebookAux {
     // whole-pass kernel, CTA 0: nanoseconds spent in [tiles, barrier 1, fold, barrier 2, update,
     // barrier 3], summed over steps (diagnostics; scripts/prof_train_pass.py reads them)
     unsigned long long phase_ns[6];
+    // PIXIE_PROFILE builds only (make prof): SM cycles warp 0 of CTA 0 spent per tile in
+    // [wait X, norm pass, accumulator wait + two passes, resolve, fix-ups, accumulate work], the
+    // number of tiles it handled, and [7] the whole accumulate call (group barrier wait + work)
+    unsigned long long tile_cyc[8];
 };
+static_assert(sizeof(CodebookAux) <= 256, "the workspace reserves 256 bytes for the control block");
 
 // Host-side plan of the tensor-core BMU kernel for one (C, K).
 struct TcPlan {
@@ -56,41 +62,27 @@ struct TcPlan {
     uint32_t stage_bytes, wimg_bytes;
     uint32_t off_bias;  // bias block inside the image: Ntot rows x 8 columns, no-swizzle core matrices
     uint32_t off_ones, off_x, off_bar, off_pairs;
-    uint32_t off_acc, off_lab;  // fused accumulation (train mode): NG x K x (C+1) fp32 tables, then
-                                // NG x sort_stride bytes of per-group sort scratch (SortLayout)
-    uint32_t sort_stride;
+    uint32_t off_acc, off_cnt, off_lab;  // fused accumulation (train mode), at off_acc: NG x K x
+                                // tab_pitch(C) fp32 group tables when they fit (tab_global == 0),
+                                // NG x K int32 node counts (off_cnt), NG x 512 bytes of label rings
+    int tab_global;             // 1 = the group tables live in global memory (TcParams::partials)
     int acc;                    // 1 = this plan has room for the fused accumulation
     int pair_cap;               // pair-list capacity per epilogue warp
+    uint32_t pairs_bytes;       // bytes at off_pairs (pair lists; scratch of the end-of-step work)
     uint32_t smem_bytes;  // dynamic shared memory to request (includes 1 KiB alignment slack)
 };
 
-// Per-group scratch of the fused accumulation (train mode): the tile's 128 rows are counting-sorted
-// by label so that the rows of a node are contiguous and their sum is a register accumulation.
-//   hist32  uint32[bins]     byte w of word b = rows of warp w labelled b (bin K = rows to skip)
-//   wbase   uint8 [4][bins]  sorted position of the first row of warp w labelled b
-//   order   uint8 [128]      sorted position -> tile row
-//   slab    uint16[128]      sorted position -> label bin
-//   side    float [4][C+1]   sum (and count) of a warp's FIRST segment: its node may continue from
-//   side_lab int[4]          the previous warp's range, so it is merged after a group barrier
-struct SortLayout {
-    uint32_t nbl, bins, off_wbase, off_order, off_slab, off_side, off_sidelab, bytes;
-};
-__host__ __device__ inline SortLayout sort_layout(int C, int K)
-{
-    SortLayout s;
-    s.nbl = ((uint32_t)K + 1u + 31u) / 32u;  // bins scanned per lane
-    s.bins = 32u * s.nbl;
-    s.off_wbase = s.bins * 4u;
-    s.off_order = s.off_wbase + 4u * s.bins;
-    s.off_slab = s.off_order + 128u;
-    s.off_side = s.off_slab + 256u;
-    s.off_sidelab = s.off_side + (4u * (uint32_t)(C + 1) * 4u + 15u) / 16u * 16u;
-    s.bytes = s.off_sidelab + 16u;
-    return s;
-}
+// Train-mode statistics.  Global tables (group tables that do not fit on chip, CTA parts):
+// [K][part_pitch(C)] fp32 -- channel sums, the count in column C.  Shared-memory group tables:
+// [K][tab_pitch(C)] fp32, sums only.  Both pitches are multiples of four floats: the accumulate
+// moves whole 16-byte chunks.
+__host__ __device__ inline int part_pitch(int C) { return (C + 1 + 3) & ~3; }
+__host__ __device__ inline int tab_pitch(int C) { return (C + 3) & ~3; }
 
-// acc = true: also reserve per-group fp32 accumulators for the fused per-node sums (train mode).
-// PIXIE_TC_STAGES (environment, experiments only) caps the pipeline depth.
+// acc = true: a plan for the fused per-node sums (train mode): per-group fp32 tables in shared
+// memory when they fit beside the pipeline, else in global memory (tab_global).  PIXIE_TC_STAGES
+// caps the pipeline depth, PIXIE_TAB_GLOBAL=1/0 forces / forbids global tables (environment,
+// experiments only).
 TcPlan make_tc_plan(int C, int K, bool acc = false);
 
 struct TcParams {
@@ -103,9 +95,12 @@ struct TcParams {
     int compact_labels;
     unsigned long long *stats;  // may be null
     CodebookAux *ctl;           // fixup_count lives here
-    // fused per-node sums (null = plain assignment): per-CTA partials [grid][K][C+1] fp32, folded
-    // into SN [K][C+1] fp64 behind a grid barrier on ctl->sums_sync
+    // fused per-node sums (partials == null: plain assignment).  partials: the group tables,
+    // [grid x NG] tables accumulated into by red.global.add during the tiles; parts: [grid] tables,
+    // each CTA's groups added up at the end of a step; SN [K][C+1] fp64: the fold of all parts
+    // (behind a grid barrier on ctl->grid_sync)
     float *partials;
+    float *parts;
     double *SN;
     // whole-pass mode (nsteps > 1 or apply != 0): the kernel runs `nsteps` mini-batch steps itself,
     // step t visiting the tiles whose GLOBAL index is congruent to (t0 + t) % B, and after each
@@ -122,11 +117,15 @@ struct TcParams {
     double *W64;           // [K x C] master codebook
     float *W32;            // [K x C] fp32 copy
     float *wimg_rw;        // the codebook image again, writable (rows < K are rewritten per step)
-    // multi-GPU whole-pass mode: every rank's exchange buffer ([2][K x (C+1)] fp64 ping-pong + one
-    // uint32 flag per source rank), mapped into this process (NVLink peer memory)
+    // multi-GPU whole-pass mode: every rank's exchange buffer (layout: exchange_slice() in
+    // bmu_tc_kernel.cuh; size: pixie_peer_buffer_bytes), mapped into this process (NVLink peer memory)
     int world, rank;
     uint32_t flag_base;    // flags only grow: step st of this launch signals flag_base + st + 1
     double *peer_buf[8];
+    int dbg_step0;         // PIXIE_PROFILE builds: first of the two steps whose events are traced
+    unsigned long long *trace;  // ... into this buffer (null in production builds)
+    unsigned int *trace_count;
+    int dbg_flags;         // experiments (PIXIE_DBG_FLAGS); 4 = per-step printf in PIXIE_PROFILE builds
     float delta_scale;     // 1 in production; tests shrink the candidate window to probe its margin
     TcPlan plan;
 };

@@ -8,6 +8,7 @@
 #include <float.h>
 
 #include "common.cuh"
+#include "som_update.cuh"
 
 namespace pixie {
 
@@ -362,53 +363,20 @@ cudaError_t launch_cluster_sums(const float *X, int64_t n, int C, int64_t ldX,
 
 // ------------------------------------------------------------------------------------------------
 // batch-SOM update (fp64 restatement in oracle/pixie_oracle.c
-// oracle_som_batch).  One CTA per node k, threads over channels.
+// oracle_som_batch): som_update_nodes (som_update.cuh), the function the whole-pass training kernel
+// runs at the end of every step, on its own grid -- CTA j updates nodes j, j + grid, ...
 // ------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(128)
+constexpr int kApplyThreads = 256;
+
+__global__ void __launch_bounds__(kApplyThreads)
 som_apply_kernel(double *__restrict__ W64, float *__restrict__ W32, const double *__restrict__ SN,
                  int xdim, int ydim, int C, double inv2s2, double alpha)
 {
     extern __shared__ double s_dyn[];
-    const int K = xdim * ydim;
-    double *s_h = s_dyn;       // [K] H[k, b] * (n_b > 0) for this CTA's node k
-    double *s_cnt = s_h + K;   // [K] n_b
-    const int k = blockIdx.x;
-    const int kx = k / ydim, ky = k % ydim;
-    for (int b = threadIdx.x; b < K; b += blockDim.x) {
-        const int dx = abs(kx - b / ydim), dy = abs(ky - b % ydim);
-        const double d = (double)(dx > dy ? dx : dy);
-        const double cnt = SN[(size_t)b * (C + 1) + C];
-        s_cnt[b] = cnt;
-        s_h[b] = cnt == 0.0 ? 0.0 : exp(-d * d * inv2s2);  // empty nodes are skipped, as the oracle does
-    }
-    __syncthreads();
-    // den_k = sum_b H[k,b] n_b in node order (every thread computes it: K is a few hundred)
-    double den = 0.0;
-    for (int b = 0; b < K; ++b) den += s_h[b] * s_cnt[b];
-    const double beta = den > 0.0 ? 1.0 - pow(1.0 - alpha, den) : 0.0;
-    for (int c = threadIdx.x; c < C; c += blockDim.x) {
-        double w = W64[(size_t)k * C + c];
-        if (den > 0.0) {
-            // sequential in b (the order the whole-pass kernel and the oracle use); the loads are
-            // issued 16 at a time so that the chain of adds does not wait for L2 once per node
-            // (K = 400: 99 us per launch with one load in flight per iteration)
-            double num = 0.0;
-            const double *col = SN + c;
-            const size_t ld = (size_t)(C + 1);
-            int b = 0;
-            for (; b + 16 <= K; b += 16) {
-                double v[16];
-#pragma unroll
-                for (int u = 0; u < 16; ++u) v[u] = __ldg(col + (size_t)(b + u) * ld);
-#pragma unroll
-                for (int u = 0; u < 16; ++u) num += s_h[b + u] * v[u];
-            }
-            for (; b < K; ++b) num += s_h[b] * __ldg(col + (size_t)b * ld);
-            w += beta * (num / den - w);
-            W64[(size_t)k * C + c] = w;
-        }
-        W32[(size_t)k * C + c] = (float)w;
-    }
+    som_update_nodes(
+        SN, W64, W32, xdim * ydim, C, ydim, inv2s2, alpha, (int)blockIdx.x, (int)gridDim.x,
+        (int)threadIdx.x, kApplyThreads, s_dyn, [] { __syncthreads(); },
+        [](int, int, float) {}, [](int, int, double, bool) {});
 }
 
 cudaError_t launch_som_apply(double *W64, float *W32, const double *SN, int xdim, int ydim, int C,
@@ -416,8 +384,14 @@ cudaError_t launch_som_apply(double *W64, float *W32, const double *SN, int xdim
 {
     const double inv2s2 = 1.0 / (2.0 * sigma * sigma);
     const int K = xdim * ydim;
-    som_apply_kernel<<<K, 128, (size_t)2 * K * sizeof(double), stream>>>(W64, W32, SN, xdim, ydim, C,
-                                                                      inv2s2, alpha);
+    const size_t smem = som_update_scratch_bytes(C, K);
+    if (smem > 48 * 1024) {
+        cudaError_t e = cudaFuncSetAttribute(som_apply_kernel,
+                                             cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+    }
+    som_apply_kernel<<<K < 148 ? K : 148, kApplyThreads, smem, stream>>>(W64, W32, SN, xdim, ydim, C,
+                                                                         inv2s2, alpha);
     count_launch();
     return cudaGetLastError();
 }

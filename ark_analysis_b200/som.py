@@ -8,6 +8,7 @@ device or without the built library these functions raise.
 """
 import ctypes
 import os
+import threading
 
 import numpy as np
 import torch
@@ -41,9 +42,13 @@ def default_radius(xdim, ydim):
 
 
 def init_codebook_indices(n, K, seed):
-    """Seeded choice of K distinct rows for the initial codebook.  Raises ValueError when n < K,
-    like ``numpy.random.choice(..., replace=False)`` does inside the reference dependency."""
-    return np.random.default_rng(seed).choice(n, K, replace=False)
+    """Seeded choice of K distinct rows for the initial codebook, as the reference dependency
+    draws it: numpy's LEGACY generator seeded with ``seed``, ``choice(n, K, replace=False)``
+    (pyFlowSOM seeds the global ``np.random``; ``RandomState(seed)`` is the same stream without the
+    side effect), so the same seed starts from the same K rows as the reference.  Raises ValueError
+    when n < K, like the reference.  Cost: the legacy ``choice`` permutes ``arange(n)`` (8 n bytes,
+    ~2 s per 2e8 rows) exactly as it does inside the reference."""
+    return np.random.RandomState(seed).choice(n, K, replace=False)
 
 
 def default_batches(n):
@@ -90,9 +95,14 @@ _ws_cache = {}
 
 
 def _workspace(n_visit, C, K, device):
-    """Per (device, stream) cached workspace, grown on demand."""
+    """Per (device, stream, host thread) cached workspace, grown on demand.
+
+    The workspace holds the control block the kernels of one call chain share (codebook norms,
+    fix-up counter: memset -> prep -> BMU -> fix-up are separate launches), so two host threads
+    must never enqueue on the same one: ``cluster_pixels(multiprocess=True)`` labels FOVs from a
+    thread pool and ctypes releases the GIL during the calls."""
     need = _native.lib().pixie_workspace_bytes(int(n_visit), int(C), int(K))
-    key = (device.index, torch.cuda.current_stream(device).cuda_stream)
+    key = (device.index, torch.cuda.current_stream(device).cuda_stream, threading.get_ident())
     ws = _ws_cache.get(key)
     if ws is None or ws.numel() < need:
         ws = torch.empty(need, dtype=torch.uint8, device=device)
@@ -360,21 +370,31 @@ def train_som(X, W0, xdim, ydim, rlen=1, alpha_range=(0.05, 0.01), radius_range=
     import torch.distributed as dist
     # Preferred: the whole run in ONE persistent kernel per rank, the per-step statistics summed
     # across GPUs inside the kernel over NVLink peer memory (symmetric memory mapped by torch).
+    # The choice is COLLECTIVE: a rank that spun in the in-kernel handshake while another rank sat
+    # in an NCCL all-reduce would hang both, so every rank reports whether it can take the peer
+    # path and the minimum decides (the all-reduce doubles as the launch rendezvous).
     peers = _peer_exchange(K, C, dev, group)
-    if peers is not None:
+    L = _native.lib()
+    mine = peers is not None and L.pixie_som_train_peers_supported(
+        int(C), int(K), int(ld), int(X.data_ptr() % 16 == 0 or n == 0)) == 1
+    vote = torch.tensor([1 if mine else 0], dtype=torch.int32, device=dev)
+    dist.all_reduce(vote, op=dist.ReduceOp.MIN, group=group)
+    use_peers = bool(int(vote.item()))
+    global last_exchange_path
+    last_exchange_path = "peer" if use_peers else "nccl"
+    if use_peers:
         ptrs, base = peers.claim(int(rlen) * B)
         with torch.cuda.device(dev):
             ws = _workspace(0, C, K, dev)
             arr = (ctypes.c_uint64 * len(ptrs))(*ptrs)
-            rc = _native.lib().pixie_som_train_peers_f32(
+            rc = L.pixie_som_train_peers_f32(
                 _ptr(X), n, C, ld, _ptr(W64), _ptr(W32), _ptr(SN), xdim, ydim, int(rlen), B,
                 float(alpha_range[0]), float(alpha_range[1]), float(radius_range[0]),
                 float(radius_range[1]), int(tile_offset), dist.get_world_size(group),
                 dist.get_rank(group), arr, base, _ptr(ws), ws.numel(), flags, _stream(dev))
-        if rc == 0:
-            return W64
-        if rc != -4:  # anything but "shape not supported" is an error
-            _native.check(rc, "pixie_som_train_peers_f32")
+        # every rank agreed to launch: a refusal here would leave the others waiting -> raise
+        _native.check(rc, "pixie_som_train_peers_f32")
+        return W64
     # Fallback: one accumulate launch, one NCCL all-reduce and one apply launch per step.
     som_apply(W64, W32, SN, xdim, ydim, 1.0, 0.0)  # W32 = fp32(W64)
     run_training_steps(
@@ -383,6 +403,11 @@ def train_som(X, W0, xdim, ydim, rlen=1, alpha_range=(0.05, 0.01), radius_range=
         allreduce=lambda stats: dist.all_reduce(stats, op=dist.ReduceOp.SUM, group=group),
         apply=lambda stats, sigma, alpha: som_apply(W64, W32, stats, xdim, ydim, sigma, alpha))
     return W64
+
+
+# "peer" / "nccl": how the last multi-GPU train_som call exchanged its statistics (bench.py
+# records it, the 2-GPU test asserts it)
+last_exchange_path = None
 
 
 class _PeerExchange:

@@ -57,6 +57,10 @@ const char *pixie_error_string(int code);
 unsigned long long pixie_kernel_launches(void);
 /* number of CUDA devices visible, or a negative error */
 int pixie_device_count(void);
+/* Diagnostic builds only (make prof, -DPIXIE_PROFILE): copies the kernel event trace to the host
+ * (two uint64 per event: key, globaltimer ns) and resets it.  Returns the number of events;
+ * always 0 in the production build. */
+int pixie_debug_trace(unsigned long long *out_host, int max_events);
 
 /* Bytes of device workspace pixie_bmu_f32 / pixie_som_accum_f32 need for these shapes. */
 size_t pixie_workspace_bytes(int64_t n, int32_t C, int32_t K);
@@ -154,15 +158,21 @@ int pixie_som_train_f32(const float *X, int64_t n, int32_t C, int64_t ldX, doubl
 
 /*
  * Multi-GPU form of pixie_som_train_f32: one call per rank (one process per GPU), all ranks at the
- * same time.  X is this rank's row shard, whose first row is GLOBAL tile `tile_offset`.  The
- * per-step statistics are summed across ranks INSIDE the training kernel over NVLink peer memory
- * (no NCCL call, no host synchronisation): `peer_bufs` is a HOST array of `world` device pointers,
- * entry r being rank r's exchange buffer mapped into this process (CUDA IPC / symmetric memory),
- * each at least pixie_peer_buffer_bytes(C, K) bytes, zero-initialised once.  `flag_base` must grow
- * by at least rlen * batches_per_pass between successive calls on the same buffers.  Every rank
- * ends with the bit-identical codebook.  Returns PIXIE_ERR_UNSUPPORTED when the shape does not fit
- * the persistent kernel (the caller then runs pixie_som_accum_f32 + all-reduce + apply per step).
+ * same time.  X is this rank's row shard, whose first row is GLOBAL tile `tile_offset` (n == 0 is
+ * allowed: a rank without rows still takes part in every exchange).  The per-step statistics are
+ * summed across ranks INSIDE the training kernel over NVLink peer memory (no NCCL call, no host
+ * synchronisation): every CTA pushes its slice of the folded table into every rank's exchange
+ * buffer, raises a per-slice flag there and adds the `world` slices it received in rank order.
+ * `peer_bufs` is a HOST array of `world` device pointers, entry r being rank r's exchange buffer
+ * mapped into this process (CUDA IPC / symmetric memory), each at least
+ * pixie_peer_buffer_bytes(C, K) bytes, zero-initialised once.  `flag_base` must grow by at least
+ * rlen * batches_per_pass between successive calls on the same buffers.  Every rank ends with the
+ * bit-identical codebook.  The ranks must AGREE to call it: pixie_som_train_peers_supported()
+ * tells a rank whether its shape / alignment fits (1) or not (0); a caller all-reduces (min) that
+ * answer and otherwise runs pixie_som_accum_f32 + all-reduce + pixie_som_apply_f64 per step.
+ * Returns PIXIE_ERR_UNSUPPORTED when called for a shape without a persistent plan.
  */
+int pixie_som_train_peers_supported(int32_t C, int32_t K, int64_t ldX, int32_t x_aligned16);
 size_t pixie_peer_buffer_bytes(int32_t C, int32_t K);
 int pixie_som_train_peers_f32(const float *X, int64_t n, int32_t C, int64_t ldX, double *W64,
                               float *W32, double *SN, int32_t xdim, int32_t ydim, int32_t rlen,

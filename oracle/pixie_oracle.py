@@ -69,10 +69,14 @@ def default_radius(xdim, ydim):
 
 
 def init_codebook_indices(n, K, seed):
-    """Seeded choice of K distinct data rows for the initial codebook.  pyFlowSOM seeds numpy's
-    legacy global RNG (Appendix A, unverified); the B200 path and this oracle both use
-    ``default_rng(seed).choice`` so that n ~ 1e9 does not allocate a permutation of n."""
-    return np.random.default_rng(seed).choice(n, K, replace=False)
+    """Seeded choice of K distinct data rows for the initial codebook: pyFlowSOM seeds numpy's
+    LEGACY global RNG with ``seed`` and draws ``np.random.choice(n, K, replace=False)`` (SURVEY.md
+    Appendix A; ark's comment at pixel_som_clustering.py:86 says the seed is consumed there).
+    ``RandomState(seed)`` is the same generator without touching the global state.  Evidence beyond
+    the recollection: the reference's own test_train_cell_som (cell_som_clustering_test.py:157,
+    `assert not np.all(cell_weights < 1)`, data seeded 24 by pytest-randomly) holds for this init
+    and FAILS for ``default_rng(seed).choice`` (tests/test_reference_suite.py)."""
+    return np.random.RandomState(seed).choice(n, K, replace=False)
 
 
 def map_data_to_nodes(nodes, newdata):

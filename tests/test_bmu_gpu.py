@@ -312,3 +312,39 @@ def test_candidate_window_has_margin(monkeypatch):
         assert torch.equal(lab, ref)
         flagged.append(int(stats[0]))  # PIXIE_STAT_ROWS_FLAGGED
     assert flagged[1] < 0.6 * flagged[0]
+
+
+def test_concurrent_host_threads_share_nothing():
+    """cluster_pixels(multiprocess=True) labels FOVs from a thread pool; ctypes releases the GIL, so
+    the memset -> prep -> BMU -> fix-up chains of several threads interleave on one stream.  Each
+    thread must own its control block: a shared one lets another thread's memset zero the codebook
+    norm (candidate window collapses, near-ties get the tf32 winner) or the fix-up counter (NaN rows
+    keep the sentinel).  Near-tie rows and NaN rows against the exact kernel, many times over."""
+    import threading
+    C, K, n = 32, 100, 128 * 64 + 5
+    X = pixie_like(n, C, seed=99)
+    W = X[np.random.default_rng(3).choice(n, K, replace=False)].copy()
+    X[::97] = W[np.arange(len(X[::97])) % K]                      # rows equal to nodes
+    W[1::2] = W[::2] * (1 + 2.0 ** -20)                           # pairs of near-identical nodes
+    X[5::211, 3] = np.nan                                         # rows for the fix-up kernel
+    Xd = S.to_device_matrix(X)
+    Wd = torch.from_numpy(W).cuda()
+    want = S.bmu(Xd, Wd, flags=S.FLAG_FORCE_EXACT).cpu().numpy()
+    np.testing.assert_array_equal(want, oracle.map_data_to_nodes_f32(W, X)[0])
+    errors = []
+
+    def worker():
+        try:
+            for _ in range(40):
+                got = S.bmu(Xd, Wd).cpu().numpy()
+                if not np.array_equal(got, want):
+                    errors.append(int((got != want).sum()))
+        except Exception as exc:  # noqa: BLE001
+            errors.append(repr(exc))
+
+    threads = [threading.Thread(target=worker) for _ in range(8)]
+    for t in threads:
+        t.start()
+    for t in threads:
+        t.join()
+    assert not errors, errors[:5]
