@@ -6,13 +6,12 @@ run on it unchanged.  The arithmetic runs on the B200 kernels.
 
 One deliberate difference: ``multiprocess=True`` does not spawn processes (a process pool would
 build one CUDA context per worker and pickle the training table to each).  FOVs are handed to a
-thread pool of ``batch_size`` workers instead: Feather reads and writes overlap, GPU calls are
-serialised by the library, and ``som_clusters_seen`` is updated in this process (the reference
-loses those updates in its child processes).
+thread pool of ``batch_size`` workers instead: Feather reads and writes overlap, every worker thread
+enqueues its kernels on its own workspace (``som._workspace``), and ``som_clusters_seen`` is
+updated in this process (the reference loses those updates in its child processes).
 """
 import os
 from concurrent.futures import ThreadPoolExecutor
-from functools import partial
 from shutil import move, rmtree
 from typing import Any, Callable, Tuple
 
@@ -105,90 +104,105 @@ def _sample_fov_columns(base_dir, data_dir, data_files):
     return [c for c in sample_cols if c not in meta]
 
 
+class _LabelRun:
+    """One pass of SOM label assignment over the FOV files of ``data_path``.
+
+    The labelled tables are written to ``data_path + '_temp'``, which replaces ``data_path`` when
+    the pass is over: an interrupted pass leaves both directories behind, and the next call only
+    labels the FOVs that have no ``pixel_som_cluster`` column yet (the reference's restart
+    protocol, pixel_som_clustering.py:220-289, pixel_cluster_utils.py:419-478)."""
+
+    def __init__(self, base_dir, data_dir, pixel_pysom, overwrite, num_parallel_pixels):
+        self.base_dir, self.data_dir = base_dir, data_dir
+        self.data_path = os.path.join(base_dir, data_dir)
+        self.temp_path = self.data_path + '_temp'
+        self.pysom = pixel_pysom
+        self.overwrite = overwrite
+        self.num_parallel_pixels = num_parallel_pixels
+        self.done = 0
+
+    def pending(self, fovs):
+        """FOVs of the master list still to label, sorted (every run sees the same order)."""
+        if self.overwrite:
+            print('Overwrite flag set, reassigning SOM cluster labels to all FOVs')
+            self.pysom.som_clusters_seen = set()
+            os.mkdir(self.temp_path)
+            candidates = io_utils.remove_file_extensions(
+                io_utils.list_files(self.data_path, substrs='.feather'))
+        else:
+            candidates = pixel_cluster_utils.find_fovs_missing_col(
+                self.base_dir, self.data_dir, 'pixel_som_cluster')
+        return sorted(set(candidates) & set(fovs))
+
+    def label(self, fov):
+        return run_pixel_som_assignment(self.data_path, self.pysom, self.overwrite,
+                                        self.num_parallel_pixels, fov)
+
+    def account(self, results, total, every=None):
+        """Book a batch of ``(fov, status)`` results: corrupted FOVs are reported and not counted;
+        progress is printed per batch, or every ``every`` FOVs and at the end."""
+        for fov, status in results:
+            if status == 1:
+                print("The data for FOV %s has been corrupted, skipping" % fov)
+            else:
+                self.done += 1
+        if every is None or self.done % every == 0 or self.done == total:
+            print("Processed %d fovs" % self.done)
+
+    def commit(self):
+        rmtree(self.data_path, onerror=_ignore_extended_attributes)
+        move(self.temp_path, self.data_path)
+
+
 def cluster_pixels(fovs, base_dir, pixel_pysom, data_dir='pixel_mat_data',
                    multiprocess=False, batch_size=5, num_parallel_pixels=1000000,
                    overwrite=False):
     """Assign SOM cluster labels to the full pixel data of every FOV; the labelled (and
     normalised) tables replace the files in ``data_dir``."""
-    data_path = os.path.join(base_dir, data_dir)
-    io_utils.validate_paths([data_path])
-
+    run = _LabelRun(base_dir, data_dir, pixel_pysom, overwrite, num_parallel_pixels)
+    io_utils.validate_paths([run.data_path])
     if pixel_pysom.weights is None:
         raise ValueError("Using untrained pixel_pysom object, please invoke train_pixel_som first")
 
-    data_files = io_utils.list_files(data_path, substrs='.feather')
+    data_files = io_utils.list_files(run.data_path, substrs='.feather')
     io_utils.verify_in_list(provided_fovs=fovs,
                             subsetted_fovs=io_utils.remove_file_extensions(data_files))
 
     # norm values, weights and data must agree on the channel columns AND their order
     channel_cols = _sample_fov_columns(base_dir, data_dir, data_files)
-    io_utils.verify_same_elements(
-        enforce_order=True,
-        norm_vals_columns=pixel_pysom.norm_data.columns.values,
-        pixel_data_columns=channel_cols)
-    io_utils.verify_same_elements(
-        enforce_order=True,
-        pixel_som_weights_columns=pixel_pysom.weights.columns.values,
-        pixel_data_columns=channel_cols)
+    for name, frame in (("norm_vals_columns", pixel_pysom.norm_data),
+                        ("pixel_som_weights_columns", pixel_pysom.weights)):
+        io_utils.verify_same_elements(enforce_order=True, **{name: frame.columns.values},
+                                      pixel_data_columns=channel_cols)
 
-    if overwrite:
-        print('Overwrite flag set, reassigning SOM cluster labels to all FOVs')
-        pixel_pysom.som_clusters_seen = set()
-        os.mkdir(data_path + '_temp')
-        fovs_list = io_utils.remove_file_extensions(
-            io_utils.list_files(data_path, substrs='.feather'))
-    else:
-        fovs_list = pixel_cluster_utils.find_fovs_missing_col(
-            base_dir, data_dir, 'pixel_som_cluster')
-
-    # only FOVs of the master list; keep a deterministic order
-    wanted = set(fovs)
-    fovs_list = sorted(f for f in set(fovs_list) if f in wanted)
-
-    if len(fovs_list) == 0:
+    todo = run.pending(fovs)
+    if not todo:
         print("There are no more FOVs to assign SOM labels to, skipping")
         return
-
-    if len(fovs_list) < len(fovs):
+    if len(todo) < len(fovs):
         print("Restarting SOM label assignment from fov %s, "
-              "%d fovs left to process" % (fovs_list[0], len(fovs_list)))
-
-    fovs_processed = 0
-    fov_data_func = partial(
-        run_pixel_som_assignment, data_path, pixel_pysom, overwrite, num_parallel_pixels)
+              "%d fovs left to process" % (todo[0], len(todo)))
 
     print("Mapping pixel data to SOM cluster labels")
-
     if multiprocess:
-        with ThreadPoolExecutor(max_workers=max(1, int(batch_size))) as pool:
-            for start in range(0, len(fovs_list), batch_size):
-                fov_batch = fovs_list[start:start + batch_size]
-                for fs in pool.map(fov_data_func, fov_batch):
-                    if fs[1] == 1:
-                        print("The data for FOV %s has been corrupted, skipping" % fs[0])
-                        fovs_processed -= 1
-                fovs_processed += len(fov_batch)
-                print("Processed %d fovs" % fovs_processed)
+        # a thread pool, not processes (module docstring): one batch of FOVs in flight at a time
+        width = max(1, int(batch_size))
+        with ThreadPoolExecutor(max_workers=width) as pool:
+            for lo in range(0, len(todo), width):
+                run.account(pool.map(run.label, todo[lo:lo + width]), len(todo))
     else:
-        for fov in fovs_list:
-            fov_status = fov_data_func(fov)
-            if fov_status[1] == 1:
-                print("The data for FOV %s has been corrupted, skipping" % fov_status[0])
-                fovs_processed -= 1
-            fovs_processed += 1
-            if fovs_processed % 10 == 0 or fovs_processed == len(fovs_list):
-                print("Processed %d fovs" % fovs_processed)
-
-    # the temp directory becomes the data directory
-    rmtree(data_path, onerror=_ignore_extended_attributes)
-    move(data_path + '_temp', data_path)
+        for fov in todo:
+            run.account([run.label(fov)], len(todo), every=10)
+    run.commit()
 
 
 def _ignore_extended_attributes(func: Callable, filename: str, exc_info: Tuple[Any, Any, Any]):
     """rmtree error handler: tolerate macOS extended-attribute files ("._*") that vanish."""
-    is_meta_file = os.path.basename(filename).startswith("._")
-    if not (func is os.unlink and is_meta_file):
-        raise
+    if func is os.unlink and os.path.basename(filename).startswith("._"):
+        return
+    if isinstance(exc_info[1], BaseException):
+        raise exc_info[1]
+    raise  # called outside an error (the reference's test does): RuntimeError, as there
 
 
 def generate_som_avg_files(fovs, channels, base_dir, pixel_pysom, data_dir='pixel_data_dir',

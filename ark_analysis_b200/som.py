@@ -500,9 +500,15 @@ def train_som_online(X, W0, xdim, ydim, rlen=1, alpha_range=(0.05, 0.01), radius
     return W64, int(done.item())
 
 
-# "batch" = the B200 production algorithm; "online" = the reference's
-# sequential rule, bit-exact to its restatement (parity mode, one CTA, does not shard)
-DEFAULT_ALGORITHM = os.environ.get("PIXIE_SOM_ALGORITHM", "batch")
+# "batch"  = the B200 production algorithm: mini-batch batch SOM, shards
+#            over GPUs, a different algorithm from the reference's (weights are NOT comparable);
+# "online" = the reference's own sequential rule on the device, bit-exact to its restatement
+#            (one CTA, ~3 us per sample, does not shard);
+# "auto"   = online while the run is short enough to be sequential (rlen * n samples at most
+#            ONLINE_MAX_ITERS: every table of the reference's tests, small cell tables), batch
+#            beyond that (pixel tables, large cell tables).
+DEFAULT_ALGORITHM = os.environ.get("PIXIE_SOM_ALGORITHM", "auto")
+ONLINE_MAX_ITERS = int(os.environ.get("PIXIE_ONLINE_MAX_ITERS", str(1 << 16)))
 
 
 def som(data, xdim=10, ydim=10, rlen=10, alpha_range=(0.05, 0.01), radius_range=None, seed=None,
@@ -510,9 +516,18 @@ def som(data, xdim=10, ydim=10, rlen=10, alpha_range=(0.05, 0.01), radius_range=
     """Drop-in for ``pyFlowSOM.som`` as ark calls it (cluster_helpers.py:106-109): trains an
     xdim x ydim SOM on ``data`` [n, C] and returns the codebook as a float64 ndarray [K, C].
 
-    ``algorithm="batch"`` (default; ``DEFAULT_ALGORITHM`` / ``PIXIE_SOM_ALGORITHM``) trains the batch
-    SOM of DESIGN.md section 4; ``"online"`` runs pyFlowSOM's sequential online rule itself on the
-    device (``train_som_online``)."""
+    The initial codebook is the reference's: K rows drawn with numpy's legacy generator seeded
+    with ``seed`` (``init_codebook_indices``).  What runs next depends on ``algorithm``
+    (default ``DEFAULT_ALGORITHM`` / ``PIXIE_SOM_ALGORITHM`` = "auto"):
+
+    * ``"online"`` -- pyFlowSOM's sequential online rule itself (``train_som_online``): same
+      sample stream, same arithmetic, so the same seed gives the reference rule's weights;
+    * ``"batch"``  -- the mini-batch BATCH SOM of DESIGN.md section 4.  A different algorithm: the
+      neighbourhood is Gaussian, a step moves a node by ``1 - (1 - alpha)^den`` (``den`` = its
+      neighbourhood-weighted row count) towards the neighbourhood mean, so with mini-batches of
+      ~1e5 rows ``lr_start`` / ``lr_end`` hardly matter and a weights file is NOT reproducible
+      against the reference's.  Map quality is what is kept (tests/test_train_gpu.py);
+    * ``"auto"``   -- online when ``rlen * n <= ONLINE_MAX_ITERS`` (65,536), else batch."""
     device = torch.device(device) if device is not None else _default_device()
     data = np.asarray(data)
     if data.ndim != 2:
@@ -525,12 +540,14 @@ def som(data, xdim=10, ydim=10, rlen=10, alpha_range=(0.05, 0.01), radius_range=
     # device matrix gets the same result
     W0 = X[torch.as_tensor(idx, device=device)].to(torch.float64)
     algorithm = algorithm or DEFAULT_ALGORITHM
+    if algorithm == "auto":
+        algorithm = "online" if int(rlen) * n <= ONLINE_MAX_ITERS else "batch"
     if algorithm == "online":
         W, _ = train_som_online(X, W0, xdim, ydim, rlen=rlen, alpha_range=alpha_range,
                                 radius_range=radius_range, seed=0 if seed is None else seed)
         return W.cpu().numpy()
     if algorithm != "batch":
-        raise ValueError("algorithm must be 'batch' or 'online'")
+        raise ValueError("algorithm must be 'auto', 'batch' or 'online'")
     W = train_som(X, W0, xdim, ydim, rlen=rlen, alpha_range=alpha_range,
                   radius_range=radius_range, batches_per_pass=batches_per_pass)
     return W.cpu().numpy()

@@ -40,10 +40,25 @@ if MODULES == "reference":
     sys.path.insert(0, os.path.join(ROOT, "baseline", "_ref"))
 else:
     compat.install(force=True)
+    # The reference's cluster_helpers.py also holds the consensus (meta) clustering classes, which
+    # are outside the SOM path and not mirrored here; its test file imports them at module level.
+    # They are taken from the UNMODIFIED reference module, loaded under a private name.
+    import importlib.util
+    from ark_analysis_b200 import cluster_helpers as _ours
+    _spec = importlib.util.spec_from_file_location(
+        "_reference_cluster_helpers",
+        os.path.join(ROOT, "baseline", "_ref", "ark", "phenotyping", "cluster_helpers.py"))
+    _refmod = importlib.util.module_from_spec(_spec)
+    _spec.loader.exec_module(_refmod)
+    for _name in ("PixieConsensusCluster", "verify_unique_meta_clusters"):
+        if not hasattr(_ours, _name):
+            setattr(_ours, _name, getattr(_refmod, _name))
     if BACKEND == "oracle":
         import pyFlowSOM as _cpu  # tests/ref_shims_cpu
-        from ark_analysis_b200 import cluster_helpers as _ch
-        _ch.som, _ch.map_data_to_nodes = _cpu.som, _cpu.map_data_to_nodes
+        from ark_analysis_b200 import som as _som
+        _som.som = lambda data, xdim=10, ydim=10, rlen=10, alpha_range=(0.05, 0.01), seed=None, \
+            **kw: _cpu.som(data, xdim, ydim, rlen, alpha_range, seed=seed)
+        _som.map_data_to_nodes = lambda nodes, newdata, **kw: _cpu.map_data_to_nodes(nodes, newdata)
 
 try:
     pd.set_option("future.infer_string", False)

@@ -86,8 +86,15 @@ class TestPixelSOMCluster:
             warnings.simplefilter("error")
             pysom.train_som()
         X = np.ascontiguousarray(pysom.train_data[self.chans].to_numpy(), np.float32)
-        ref = oracle.som_batch(X, 20, 10, rlen=1, seed=7)
-        assert np.abs(pysom.weights.values - ref).max() / np.abs(ref).max() < 1e-4
+        # a table this small trains with the reference's own online rule (som.som "auto"): the
+        # weights equal the C restatement of pyFlowSOM's C_SOM bit for bit
+        ref = oracle.som_online(X.astype(np.float64), 20, 10, rlen=1, seed=7)
+        np.testing.assert_array_equal(pysom.weights.values, ref)
+        # and the batch SOM (what a large table gets) agrees with ITS oracle
+        from ark_analysis_b200 import som as S
+        Wb = S.som(X, xdim=20, ydim=10, rlen=1, seed=7, algorithm="batch")
+        refb = oracle.som_batch(X, 20, 10, rlen=1, seed=7)
+        assert np.abs(Wb - refb).max() / np.abs(refb).max() < 1e-4
 
     @pytest.mark.parametrize("num_parallel_pixels", [10, 10000])
     def test_assign_som_clusters(self, tmp_path, num_parallel_pixels):

@@ -40,7 +40,15 @@ def _worker(rank, world, port, X, W0, out):
     labels = S.bmu(Xd, W.to(torch.float32))
     torch.cuda.synchronize()
     # the fused peer-memory path (not the NCCL fallback) must have been taken
-    assert any(v is not None for v in S._peer_cache.values()), "peer-memory exchange not used"
+    assert S.last_exchange_path == "peer", "peer-memory exchange not used"
+    # a rank WITHOUT rows (fewer tiles than ranks) still takes part in every exchange
+    small = X[:100]
+    slo, shi = distributed.tile_aligned_row_shards(small.shape[0], world)[rank]
+    Xs = S.to_device_matrix(small[slo:shi], torch.device("cuda", rank))
+    Ws = S.train_som(Xs, W0[:16], 4, 4, rlen=3, batches_per_pass=1, group=dist.group.WORLD,
+                     tile_offset=slo // 128)
+    assert S.last_exchange_path == "peer"
+    np.save(out % ("s", rank), Ws.cpu().numpy())
     # and the NCCL step loop gives the same codebook
     os.environ["PIXIE_DISABLE_PEER"] = "1"
     S._peer_cache.clear()
@@ -67,6 +75,11 @@ def test_two_gpu_training_and_assignment(tmp_path):
     assert np.abs(w0 - ref).max() / np.abs(ref).max() < 1e-4
     single = S.train_som(S.to_device_matrix(X), W0, XD, YD, rlen=2, batches_per_pass=B)
     assert np.abs(w0 - single.cpu().numpy()).max() / np.abs(ref).max() < 1e-6
+    # the shard-less rank: same codebook on both ranks, equal to the single-GPU one
+    s0, s1 = np.load(out % ("s", 0)), np.load(out % ("s", 1))
+    np.testing.assert_array_equal(s0, s1)
+    alone = S.train_som(S.to_device_matrix(X[:100]), W0[:16], 4, 4, rlen=3, batches_per_pass=1)
+    assert np.abs(s0 - alone.cpu().numpy()).max() <= 1e-9 * np.abs(s0).max()
     labels = np.concatenate([np.load(out % ("l", 0)), np.load(out % ("l", 1))])
     want, _ = oracle.map_data_to_nodes_f32(w0.astype(np.float32), X)
     np.testing.assert_array_equal(labels, want)

@@ -50,7 +50,7 @@ def test_golden_som_batch():
 
 def test_pyflowsom_shaped_som_function():
     X = pixie_like(8000, 12, seed=4).astype(np.float64)
-    W = S.som(X, xdim=5, ydim=4, rlen=2, alpha_range=(0.05, 0.01), seed=42)
+    W = S.som(X, xdim=5, ydim=4, rlen=2, alpha_range=(0.05, 0.01), seed=42, algorithm="batch")
     assert W.shape == (20, 12) and W.dtype == np.float64
     ref = oracle.som_batch(X.astype(np.float32), 5, 4, rlen=2, seed=42)
     assert rel_err(W, ref) < RTOL
@@ -58,7 +58,7 @@ def test_pyflowsom_shaped_som_function():
     # cell_som_clustering_test.py:97: trained weights < 1 on <= 1 data)
     assert W.min() >= X.min() - 1e-6 and W.max() <= X.max() + 1e-6
     with pytest.raises(ValueError):
-        S.som(X[:10], xdim=5, ydim=4, rlen=1, seed=1)  # fewer rows than nodes
+        S.som(X[:10], xdim=5, ydim=4, rlen=1, seed=1)  # fewer rows than nodes (any algorithm)
 
 
 def test_step_functions_accumulate_and_apply():
@@ -96,7 +96,7 @@ def test_map_quality_is_as_good_as_the_online_reference_rule():
     """The reference trains an ONLINE SOM; ours is a batch SOM (SURVEY.md section 7 hard part 1).
     Weight parity across the two is meaningless; map quality is what must hold."""
     X = pixie_like(30000, 16, seed=8)
-    Wb = S.som(X, xdim=10, ydim=10, rlen=1, seed=42)
+    Wb = S.som(X, xdim=10, ydim=10, rlen=1, seed=42, algorithm="batch")
     Wo = oracle.som_online(X.astype(np.float64), 10, 10, rlen=1, seed=42)
 
     def qe(W):
@@ -132,5 +132,11 @@ def test_online_som_through_the_pyflowsom_shaped_call():
     idx = oracle.init_codebook_indices(1200, 20, 11)
     want = oracle.som_online(X.astype(np.float64), 4, 5, rlen=2, seed=11, init_idx=idx)
     assert W.shape == (20, 8) and np.array_equal(W, want)
+    # "auto" (the default) takes the online rule for a table this small and the batch SOM beyond
+    # ONLINE_MAX_ITERS samples
+    assert np.array_equal(S.som(X, xdim=4, ydim=5, rlen=2, seed=11), want)
+    big = np.tile(X, (60, 1))  # 72,000 rows > 65,536
+    auto = S.som(big, xdim=4, ydim=5, rlen=1, seed=11)
+    assert np.array_equal(auto, S.som(big, xdim=4, ydim=5, rlen=1, seed=11, algorithm="batch"))
     with pytest.raises(ValueError):
         S.som(X, xdim=4, ydim=5, algorithm="nope")
