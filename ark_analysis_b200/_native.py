@@ -79,8 +79,9 @@ def lib():
         L.pixie_error_string.restype = c.c_char_p
         L.pixie_error_string.argtypes = [c.c_int]
         L.pixie_device_count.restype = c.c_int
-        L.pixie_debug_trace.restype = c.c_int
-        L.pixie_debug_trace.argtypes = [vp, c.c_int]
+        if hasattr(L, "pixie_debug_trace"):  # absent from older builds loaded via PIXIE_LIB_PATH
+            L.pixie_debug_trace.restype = c.c_int
+            L.pixie_debug_trace.argtypes = [vp, c.c_int]
         L.pixie_kernel_launches.restype = c.c_ulonglong
         L.pixie_workspace_bytes.restype = sz
         L.pixie_workspace_bytes.argtypes = [i64, i32, i32]
@@ -98,8 +99,9 @@ def lib():
                                           dbl, dbl, dbl, vp, sz, u32, vp]
         L.pixie_peer_buffer_bytes.restype = sz
         L.pixie_peer_buffer_bytes.argtypes = [i32, i32]
-        L.pixie_som_train_peers_supported.restype = c.c_int
-        L.pixie_som_train_peers_supported.argtypes = [i32, i32, i64, i32]
+        if hasattr(L, "pixie_som_train_peers_supported"):
+            L.pixie_som_train_peers_supported.restype = c.c_int
+            L.pixie_som_train_peers_supported.argtypes = [i32, i32, i64, i32]
         L.pixie_som_train_peers_f32.argtypes = [vp, i64, i32, i64, vp, vp, vp, i32, i32, i32, i32, dbl,
                                                 dbl, dbl, dbl, i64, i32, i32, vp, u32, vp, sz, u32, vp]
         L.pixie_som_train_peers_f32.restype = c.c_int

@@ -131,6 +131,16 @@ TcPlan make_tc_plan(int C, int K, bool acc)
         // (Measured: a free stage count -- 7 instead of 4 stages in train mode, made safe by an
         // extra wait for the stage's previous release -- bought nothing and cost assign 1.7 %.)
         p.nstage = p.nstage / v.NG * v.NG;
+        if (acc) {
+            // Train mode keeps loop state on the stack around the per-tile accumulate call (~370
+            // bytes x 576 threads): with all of shared memory taken the L1 left over (228 KB
+            // carve-out -> 28 KB) thrashes on it.  A pipeline one tile per group deep is enough here
+            // (the producer runs a whole step ahead anyway), so stay under the 164 KB carve-out
+            // when that is possible: cfg2 8 -> 4 stages, training pass 1.72 -> 1.56 ms.
+            const uint32_t soft = 164u * 1024u - 1024u;
+            while (p.nstage > v.NG && p.off_x + scratch + (uint32_t)p.nstage * p.stage_bytes > soft)
+                p.nstage -= v.NG;
+        }
         p.off_bar = p.off_x + (uint32_t)p.nstage * p.stage_bytes;
         p.off_pairs = p.off_bar + (uint32_t)kBarBlock;
         p.pair_cap = (int)pair_cap;

@@ -328,7 +328,7 @@ __device__ __forceinline__ void publish_labels(uint8_t *smem, uint32_t lab_off, 
 }
 
 template <int NBLK, bool TABG>
-__device__ __forceinline__ void tile_accumulate_blk(const TcParams &p, uint8_t *smem,
+__device__ __noinline__ void tile_accumulate_blk(const TcParams &p, uint8_t *smem,
                                                     uint32_t xs_addr, uint32_t tab_addr,
                                                     float *tab_g, uint32_t lab_off,
                                                     uint32_t list_addr, int quad, int lane,
@@ -594,6 +594,12 @@ __device__ __noinline__ void step_finish(const TcParams &p, int st, uint8_t *sme
         }
     };
     lap(0);  // tiles
+#ifdef PIXIE_PROFILE
+    // arrival time of every CTA at the end of its tiles, steps dbg_step0 .. +1: slots behind the
+    // 32 x 1024 event slots of the trace buffer
+    if (p.trace && tid == 0 && st >= p.dbg_step0 && st < p.dbg_step0 + 2)
+        p.trace[2u * 32u * 1024u + (unsigned)(st - p.dbg_step0) * 256u + blockIdx.x] = global_timer_ns();
+#endif
 
     // 1. this CTA's part of the statistics: its NG group tables are added in group order, the
     //    counts joined in, tables and counts cleared for the next step.
@@ -721,7 +727,7 @@ __device__ __noinline__ void step_finish(const TcParams &p, int st, uint8_t *sme
 // ------------------------------------------------------------------------------------------------
 template <int SL, int SPC, int NCH, int NG, bool ACC>
 __global__ void __launch_bounds__(NG * 128 + 64, 1)
-bmu_tc_kernel(const __grid_constant__ CUtensorMap tmX, const TcParams p)
+bmu_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ TcParams p)
 {
     constexpr int NEPI = NG * 4;            // epilogue warps
     constexpr int NCHUNK = SL * SPC;        // codebook rows per accumulator chunk

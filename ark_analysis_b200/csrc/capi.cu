@@ -260,8 +260,10 @@ int pixie_debug_trace(unsigned long long *out_host, int max_events)
 {
 #ifdef PIXIE_PROFILE
     // 32 warps x 1024 slots of two words; unused slots are zero
-    if (!pixie::g_trace || max_events < (1 << 15)) return 0;
-    if (cudaMemcpy(out_host, pixie::g_trace, (size_t)(1u << 15) * 16, cudaMemcpyDeviceToHost) != cudaSuccess)
+    // ... followed by 2 x 256 CTA arrival times (max_events must leave room: 2^15 + 256)
+    if (!pixie::g_trace || max_events < (1 << 15) + 256) return 0;
+    if (cudaMemcpy(out_host, pixie::g_trace, (size_t)(1u << 15) * 16 + 4096, cudaMemcpyDeviceToHost) !=
+        cudaSuccess)
         return -1;
     return 1 << 15;
 #else
@@ -566,11 +568,11 @@ static int launch_whole_pass(const float *X, int64_t n, int32_t C, int64_t ldX, 
     p.dbg_step0 = getenv("PIXIE_TRACE_STEP") ? atoi(getenv("PIXIE_TRACE_STEP")) : 1 << 30;
 #ifdef PIXIE_PROFILE
     if (!pixie::g_trace) {
-        cudaMalloc(&pixie::g_trace, (size_t)2 * (1u << 15) * 8);
+        cudaMalloc(&pixie::g_trace, (size_t)2 * (1u << 15) * 8 + 4096);
         cudaMalloc(&pixie::g_trace_count, 4);
         cudaMemset(pixie::g_trace_count, 0, 4);
     }
-    cudaMemsetAsync(pixie::g_trace, 0, (size_t)2 * (1u << 15) * 8, st);
+    cudaMemsetAsync(pixie::g_trace, 0, (size_t)2 * (1u << 15) * 8 + 4096, st);
     p.trace = pixie::g_trace;
     p.trace_count = pixie::g_trace_count;
 #endif
