@@ -513,65 +513,60 @@ __device__ __forceinline__ void fold_slice_sum(const TcParams &p, int nparts, in
 
 // Cross-GPU sum of this CTA's slice [e0, e1) (s_slice holds this rank's folded values).
 // Exchange buffer of a rank (torch symmetric memory, mapped on every rank):
-//   vals  double [2][8][len]        parity of the step x SOURCE rank x element
-//   flags uint32 [2][8][kSumParts]  parity x source rank x slice (= CTA) index
-// Every CTA PUSHES its slice into the vals[parity][my rank] area of every rank (plain remote stores:
-// one-way NVLink traffic, no round trip), then raises flags[parity][my rank][cta] on every rank
-// (fence.sys + store); it then waits for the same flag from every source rank in its OWN buffer
-// (local polls) and adds the eight slices in rank order -- every rank adds the same values in the
-// same order: bit-identical totals, no grid barrier, no NCCL call, no host round trip.
+//   cell uint32[4] [2][8][len]   parity of the step x SOURCE rank x element
+// a cell = {low word, tag, high word, tag} of one fp64 value, written with ONE 16-byte store.
+// Every CTA PUSHES each value of its slice into the cell [parity][my rank][e] of every other rank
+// (one-way NVLink traffic, no round trip); the owner of the same slice there polls its OWN memory
+// until both tags of the cell carry this step's number (8-byte halves are single-copy atomic, so a
+// half with the right tag holds the right data: the scheme NCCL's LL protocol uses), and adds the
+// `world` values in rank order -- every rank adds the same values in the same order: bit-identical
+// totals.  No fence, no flag round trip, no grid barrier, no NCCL call, no host round trip: the
+// cost of a step's exchange is one NVLink store latency plus the skew between the GPUs.
 // Reuse of a parity slot two steps later is safe: a rank can only reach the push of step t + 2
-// after it saw this rank's flag of step t + 1, which this CTA raised after it had read step t.
+// after it received this rank's values of step t + 1, which this CTA sent after it had read step t.
 __device__ __forceinline__ void exchange_slice(const TcParams &p, int st, int len, int e0, int e1,
                                                int tid, int nthr, const double *s_slice)
 {
-    const int par = st & 1;
-    const size_t vals_off = ((size_t)par * 8 + (size_t)p.rank) * len;
-    for (int i = tid; i < (e1 - e0) * p.world; i += nthr) {
-        const int r = i / (e1 - e0), e = e0 + (i - r * (e1 - e0));
-        double *dst = p.peer_buf[r] + vals_off + e;
-        asm volatile("st.relaxed.sys.global.f64 [%0], %1;" ::"l"(dst), "d"(s_slice[e - e0]) : "memory");
+    const int par = st & 1, ne = e1 - e0;
+    const uint32_t tag = p.flag_base + (uint32_t)st + 1u;
+    const size_t cell0 = ((size_t)par * 8 + (size_t)p.rank) * len;
+    for (int i = tid; i < ne * p.world; i += nthr) {
+        const int r = i / ne, e = e0 + (i - r * ne);
+        if (r == p.rank) continue;
+        const unsigned long long bits = (unsigned long long)__double_as_longlong(s_slice[e - e0]);
+        uint4 *dst = reinterpret_cast<uint4 *>(p.peer_buf[r]) + cell0 + e;
+        asm volatile("st.relaxed.sys.global.v4.u32 [%0], {%1, %2, %3, %4};" ::"l"(dst),
+                     "r"((uint32_t)bits), "r"(tag), "r"((uint32_t)(bits >> 32)), "r"(tag)
+                     : "memory");
     }
-    bar_sync(kBarStep, nthr);
-    const uint32_t val = p.flag_base + (uint32_t)st + 1u;
-    const size_t flags_off = (size_t)2 * 8 * len * sizeof(double);
-    if (tid < p.world) {
-        __threadfence_system();
-        uint32_t *dst = reinterpret_cast<uint32_t *>(reinterpret_cast<char *>(p.peer_buf[tid]) + flags_off) +
-                        ((size_t)par * 8 + p.rank) * kSumParts + blockIdx.x;
-        asm volatile("st.relaxed.sys.global.u32 [%0], %1;" ::"l"(dst), "r"(val) : "memory");
-        const uint32_t *src = reinterpret_cast<const uint32_t *>(
-                                  reinterpret_cast<const char *>(p.peer_buf[p.rank]) + flags_off) +
-                              ((size_t)par * 8 + tid) * kSumParts + blockIdx.x;
-        uint32_t seen, spins = 0;
-        uint64_t t0 = 0;
-        do {
-            asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(seen) : "l"(src) : "memory");
-            if (seen - val < 0x80000000u) break;  // seen >= val (wrap-safe)
-            if ((++spins & 1023u) == 0u) {
-                // a peer that never arrives (died, or took the other code path) makes this rank
-                // fail after 60 s instead of hanging; launch skew between ranks is far below that
-                const uint64_t now = global_timer_ns();
-                if (t0 == 0) t0 = now;
-                if (now - t0 > 60000000000ull) __trap();
-                __nanosleep(128);
-            }
-        } while (true);
-    }
-    bar_sync(kBarStep, nthr);
-    const double *mine = p.peer_buf[p.rank] + (size_t)par * 8 * len;
+    const uint4 *mine = reinterpret_cast<const uint4 *>(p.peer_buf[p.rank]) + (size_t)par * 8 * len;
     for (int e = e0 + tid; e < e1; e += nthr) {
-        double v[8];
-#pragma unroll
-        for (int r = 0; r < 8; ++r) {
-            v[r] = 0.0;
-            if (r < p.world)
-                asm volatile("ld.relaxed.sys.global.f64 %0, [%1];" : "=d"(v[r]) : "l"(mine + (size_t)r * len + e) : "memory");
-        }
         double a = 0.0;
-#pragma unroll
-        for (int r = 0; r < 8; ++r)
-            if (r < p.world) a += v[r];
+        for (int r = 0; r < p.world; ++r) {  // rank order
+            double v = s_slice[e - e0];
+            if (r != p.rank) {
+                const uint4 *src = mine + (size_t)r * len + e;
+                uint4 c;
+                uint32_t spins = 0;
+                uint64_t t0 = 0;
+                do {
+                    asm volatile("ld.relaxed.sys.global.v4.u32 {%0, %1, %2, %3}, [%4];"
+                                 : "=r"(c.x), "=r"(c.y), "=r"(c.z), "=r"(c.w)
+                                 : "l"(src)
+                                 : "memory");
+                    if (c.y == tag && c.w == tag) break;
+                    if ((++spins & 1023u) == 0u) {
+                        // a peer that never arrives (died, or took the other code path) makes this
+                        // rank fail after 60 s instead of hanging
+                        const uint64_t now = global_timer_ns();
+                        if (t0 == 0) t0 = now;
+                        if (now - t0 > 60000000000ull) __trap();
+                    }
+                } while (true);
+                v = __longlong_as_double((long long)(((unsigned long long)c.z << 32) | c.x));
+            }
+            a += v;
+        }
         p.SN[e] = a;
     }
 }

@@ -731,9 +731,8 @@ int pixie_som_train_f32(const float *X, int64_t n, int32_t C, int64_t ldX, doubl
 size_t pixie_peer_buffer_bytes(int32_t C, int32_t K)
 {
     if (C < 1 || K < 1) return 0;
-    // vals double [2][8][K (C+1)] + flags uint32 [2][8][kSumParts]  (exchange_slice, bmu_tc_kernel.cuh)
-    return (size_t)2 * 8 * K * (C + 1) * sizeof(double) + (size_t)2 * 8 * kSumParts * sizeof(uint32_t) +
-           256;
+    // cells uint32[4] [2][8][K (C+1)]  (exchange_slice, bmu_tc_kernel.cuh)
+    return (size_t)2 * 8 * K * (C + 1) * 16 + 256;
 }
 
 int pixie_som_train_peers_supported(int32_t C, int32_t K, int64_t ldX, int32_t x_aligned16)

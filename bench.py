@@ -9,11 +9,17 @@ Workload (config.workload): BASELINE.json configs[1] per GPU -- 50 synthetic 102
 channels, 10 x 10 SOM.  A STEP is one pass of the hot path over that data:
   (1) train   -- one training pass (num_passes=1, 32 mini-batches: BMU + per-node aggregation +
                  codebook update) over the 10 % pixel subset (5,242,880 rows per GPU); with N > 1
-                 one NCCL all-reduce of the K x (C+1) statistics per mini-batch;
+                 the per-step statistics are summed across GPUs inside the kernel (NVLink peer
+                 memory), the line says which exchange path ran;
   (2) assign  -- BMU label of every pixel (52,428,800 rows per GPU) against the trained codebook.
 `value` = pixels visited per second (train rows + assign rows, all GPUs) with the data resident in
 HBM; `e2e` = the same step through the host-buffer API (pinned host memory in, labels out).
 Weak scaling: every rank owns its own 50 FOVs.  Inputs (6.7 GB per GPU) are far larger than L2.
+
+A second block, `cfg3`, measures BASELINE.json configs[2] the same way on its per-GPU shard: 62 of
+the 500 synthetic 2048 x 2048 FOVs x 40 channels, 20 x 20 SOM (41.6 GB of pixels + the 10 %
+subset resident per GPU; at N = 8 that is the whole named configuration, below that a resident
+wave of it).  It carries its own roofline, train / assign times and exchange path.
 """
 import argparse
 import json
@@ -35,6 +41,8 @@ K = XD * YD
 BATCHES = 32
 SUBSET = 0.1
 SEED = 42
+# BASELINE.json configs[2], per-GPU shard (500 FOVs over 8 GPUs = 62.5)
+CFG3 = dict(nfov=62, hw=2048, C=40, xd=20, yd=20)
 
 
 def measured_peaks():
@@ -62,25 +70,26 @@ def workload_config(n_gpus):
 # ------------------------------------------------------------------------------------------------
 # synthetic data (distribution "P")
 # ------------------------------------------------------------------------------------------------
-def prototypes():
+def prototypes(channels=C):
     r = np.random.default_rng(12345)
-    return r.dirichlet(np.full(C, 0.3), size=30).astype(np.float32)
+    return r.dirichlet(np.full(channels, 0.3), size=30).astype(np.float32)
 
 
-def gen_fovs_device(torch, device, fov_ids, out):
-    """Fill `out` [len(fov_ids) * HW*HW, C] with Pixie-like rows, FOV f seeded 42 + f."""
-    protos = torch.from_numpy(prototypes()).to(device)
-    npx = HW * HW
+def gen_fovs_device(torch, device, fov_ids, out, hw=HW, channels=C):
+    """Fill `out` [len(fov_ids) * hw*hw, channels] with Pixie-like rows, FOV f seeded 42 + f."""
+    protos = torch.from_numpy(prototypes(channels)).to(device)
+    npx = hw * hw
     norm = None
     for i, f in enumerate(fov_ids):
         g = torch.Generator(device=device).manual_seed(SEED + int(f))
         which = torch.randint(0, protos.shape[0], (npx,), device=device, generator=g)
         x = protos[which]
-        x += torch.randn((npx, C), device=device, generator=g).abs_() * 0.05
+        x += torch.randn((npx, channels), device=device, generator=g).abs_() * 0.05
         x /= x.sum(1, keepdim=True)
         if norm is None:
             # per-channel 99.9th percentile, estimated on the first FOV (Pixie's channel norm)
-            norm = torch.stack([x[:, c].kthvalue(int(0.999 * npx)).values for c in range(C)])
+            norm = torch.stack([x[:, c].kthvalue(int(0.999 * npx)).values
+                                for c in range(channels)])
         x /= norm
         out[i * npx:(i + 1) * npx] = x
         del x, which
@@ -208,6 +217,196 @@ def run_reference(args):
 # ------------------------------------------------------------------------------------------------
 # GPU arm
 # ------------------------------------------------------------------------------------------------
+def bind_to_gpu_numa_node(local):
+    """Run this rank (and first-touch its pinned buffers) on the CPUs of the NUMA node its GPU hangs
+    off.  Returns a description for the JSON line; never fails the run."""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        bdf = pynvml.nvmlDeviceGetPciInfo(pynvml.nvmlDeviceGetHandleByIndex(local)).busId
+        bdf = (bdf.decode() if isinstance(bdf, bytes) else bdf).lower()
+        if len(bdf.split(":")[0]) == 8:
+            bdf = bdf[4:]
+        node = int(open(f"/sys/bus/pci/devices/{bdf}/numa_node").read())
+        if node < 0:
+            return {"numa_node": None, "cpus": len(os.sched_getaffinity(0))}
+        cpus = set()
+        for part in open(f"/sys/devices/system/node/node{node}/cpulist").read().strip().split(","):
+            lo, _, hi = part.partition("-")
+            cpus.update(range(int(lo), int(hi or lo) + 1))
+        cpus &= os.sched_getaffinity(0)
+        if cpus:
+            os.sched_setaffinity(0, cpus)
+        return {"numa_node": node, "cpus": len(cpus)}
+    except Exception as exc:  # noqa: BLE001 -- placement is best effort
+        return {"numa_node": None, "error": repr(exc)[:80]}
+
+
+class Workload:
+    """Resident synthetic data of one configuration on this rank + its step."""
+
+    def __init__(self, torch, S, dev, rank, world, group, nfov, hw, channels, xd, yd):
+        self.torch, self.S, self.dev, self.group = torch, S, dev, group
+        self.rank, self.world = rank, world
+        self.nfov, self.hw, self.C, self.xd, self.yd, self.K = nfov, hw, channels, xd, yd, xd * yd
+        npx = hw * hw
+        self.npx, self.n = npx, nfov * npx
+        fov_ids = list(range(rank * nfov, (rank + 1) * nfov))
+        self.X = torch.empty((self.n, channels), dtype=torch.float32, device=dev)
+        gen_fovs_device(torch, dev, fov_ids, self.X, hw, channels)
+        ntrain_fov = int(npx * SUBSET) // 128 * 128  # tile aligned per FOV
+        g = torch.Generator(device=dev).manual_seed(SEED + 1000 + rank)
+        self.Xt = torch.empty((nfov * ntrain_fov, channels), dtype=torch.float32, device=dev)
+        for i in range(nfov):
+            idx = torch.randperm(npx, device=dev, generator=g)[:ntrain_fov]
+            self.Xt[i * ntrain_fov:(i + 1) * ntrain_fov] = self.X[i * npx:(i + 1) * npx][idx]
+        self.ntrain = self.Xt.shape[0]
+        self.tile_offset = rank * (self.ntrain // 128)
+        # initial codebook: seeded rows of rank 0's subset, identical on every rank (the legacy
+        # generator permutes arange(n): a one-off outside every timed region)
+        init_idx = S.init_codebook_indices(self.ntrain, self.K, SEED)
+        self.W0 = self.Xt[torch.as_tensor(init_idx, device=dev)].to(torch.float64)
+        if world > 1:
+            import torch.distributed as dist
+            dist.broadcast(self.W0, src=0)
+        self.labels = torch.empty(self.n, dtype=torch.int32, device=dev)
+        self.W32 = None
+        self.W64 = None
+
+    def step(self, ev=None):
+        torch, S = self.torch, self.S
+        if ev:
+            ev[0].record()
+        W = S.train_som(self.Xt, self.W0, self.xd, self.yd, rlen=1, alpha_range=(0.05, 0.01),
+                        batches_per_pass=BATCHES, group=self.group, tile_offset=self.tile_offset)
+        W32 = W.to(torch.float32)
+        if ev:
+            ev[1].record()
+        S.bmu(self.X, W32, labels=self.labels)
+        if ev:
+            ev[2].record()
+        self.W64, self.W32 = W, W32
+        return W32
+
+    def describe(self, which):
+        return {
+            "workload": f"Pixie pixel SOM: {self.nfov} synthetic {self.hw}x{self.hw} FOVs x {self.C} "
+                        f"channels per GPU, {self.xd}x{self.yd} SOM (BASELINE.json {which}); step = 1 "
+                        f"training pass over the 10% subset ({BATCHES} mini-batches) + BMU "
+                        f"assignment of every pixel",
+            "fovs_per_gpu": self.nfov, "fov_shape": [self.hw, self.hw], "channels": self.C,
+            "som": [self.xd, self.yd], "assign_rows_per_gpu": self.n,
+            "train_rows_per_gpu": self.ntrain, "batches_per_pass": BATCHES, "num_passes": 1,
+            "distribution": "pixie-like (P)",
+            "parallelism": f"fov-sharded x{self.world}" if self.world > 1 else "single gpu",
+            "l2": f"inputs ({self.n * self.C * 4 / 1e9:.1f} GB/GPU) larger than L2; no flush needed",
+        }
+
+
+def timed_steps(torch, dist, wl, steps, warmup, lib):
+    """W warm-up steps, then exactly `steps` timed ones bracketed by barrier + synchronize; device
+    times from CUDA events on the launching stream, max over ranks."""
+    from ark_analysis_b200 import _native
+    S, dev, distributed = wl.S, wl.dev, wl.world > 1
+    for _ in range(max(warmup, 3)):
+        wl.step()
+    torch.cuda.synchronize()
+    # parity guard inside the bench: a window of the labels against the exact fp64 kernel
+    chk = S.bmu(wl.X[:262144], wl.W32, flags=S.FLAG_FORCE_EXACT)
+    assert torch.equal(chk, wl.labels[:262144]), "bench labels differ from the exact kernel"
+    stats = torch.zeros(S.NSTATS, dtype=torch.int64, device=dev)
+    S.bmu(wl.X, wl.W32, labels=wl.labels, stats=stats)
+    torch.cuda.synchronize()
+    flagged_frac = float(stats[_native.STAT_ROWS_FLAGGED]) / wl.n
+    if distributed:
+        dist.barrier()
+    torch.cuda.synchronize()
+    launches0 = lib.pixie_kernel_launches()
+    evs = [[torch.cuda.Event(enable_timing=True) for _ in range(3)] for _ in range(steps)]
+    t_wall0 = time.perf_counter()
+    for k in range(steps):
+        wl.step(evs[k])
+    end = torch.cuda.Event(enable_timing=True)
+    end.record()
+    torch.cuda.synchronize()
+    if distributed:
+        dist.barrier()
+    wall_ms = 1e3 * (time.perf_counter() - t_wall0)
+    launches = lib.pixie_kernel_launches() - launches0
+    total_ms = evs[0][0].elapsed_time(end)
+    train_ms = sum(e[0].elapsed_time(e[1]) for e in evs)
+    assign_ms = sum(e[1].elapsed_time(e[2]) for e in evs)
+    t = torch.tensor([total_ms, train_ms, assign_ms, wall_ms], dtype=torch.float64, device=dev)
+    if distributed:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    total_ms, train_ms, assign_ms, wall_ms = [float(v) for v in t.tolist()]
+    px_step = (wl.n + wl.ntrain) * wl.world
+    peak, peak_src = measured_peaks()
+    assign_ms_launch = assign_ms / steps
+    bytes_launch = wl.n * (4 * wl.C + 4)
+    achieved = bytes_launch / (assign_ms_launch * 1e-3) / 1e9
+    # every rank must hold the same codebook, bit for bit
+    same = True
+    if distributed:
+        gathered = [torch.empty_like(wl.W64) for _ in range(wl.world)]
+        dist.all_gather(gathered, wl.W64.contiguous())
+        same = all(torch.equal(gathered[0], g) for g in gathered[1:])
+        assert same, "ranks ended a training pass with different codebooks"
+    return {
+        "value": px_step * steps / (total_ms * 1e-3), "ms_per_step": total_ms / steps,
+        "train_pixels_per_s": wl.ntrain * wl.world * steps / (train_ms * 1e-3),
+        "assign_pixels_per_s": wl.n * wl.world * steps / (assign_ms * 1e-3),
+        "train_ms_per_step": train_ms / steps, "assign_ms_per_step": assign_ms / steps,
+        "wall_ms_per_step": wall_ms / steps, "rows_rechecked_frac": flagged_frac,
+        "exchange": (S.last_exchange_path if distributed else "none (single GPU)"),
+        "codebooks_identical_on_all_ranks": bool(same),
+        "gpu_launches": int(launches),
+        "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
+                     "frac": achieved / peak, "kernel": "bmu_tc_kernel (assign)",
+                     "bytes_per_pixel": 4 * wl.C + 4, "pixels_per_launch": wl.n,
+                     "peak_source": peak_src, "ms_per_launch": assign_ms_launch},
+    }
+
+
+def oracle_check_sampled_shard(torch, dist, wl):
+    """Trains on a small sample of every rank's shard through the SAME multi-GPU path and compares
+    the codebook with the fp64 oracle of the batch SOM run on the concatenated sample (the oracle
+    as the checker, on rank 0).  Returns the relative error."""
+    S, dev = wl.S, wl.dev
+    rows = 64 * 128
+    Xs = wl.Xt[:rows].contiguous()
+    W = S.train_som(Xs, wl.W0, wl.xd, wl.yd, rlen=1, batches_per_pass=8, group=wl.group,
+                    tile_offset=wl.rank * (rows // 128))
+    if wl.world > 1:
+        parts = [torch.empty_like(Xs) for _ in range(wl.world)]
+        dist.all_gather(parts, Xs)
+        allX = torch.cat(parts)
+    else:
+        allX = Xs
+    err = None
+    if wl.rank == 0:
+        import oracle
+        oracle.build()
+        Wo = np.ascontiguousarray(wl.W0.cpu().numpy())
+        Xh = np.ascontiguousarray(allX.cpu().numpy())
+        ref = _oracle_batch_from_codebook(oracle, Xh, Wo, wl.xd, wl.yd, 8)
+        err = float(np.abs(W.cpu().numpy() - ref).max() / np.abs(ref).max())
+        assert err < 1e-4, f"trained codebook differs from the oracle: {err}"
+    return err
+
+
+def _oracle_batch_from_codebook(oracle, X32, W0, xd, yd, B):
+    """oracle.som_batch with an explicit initial codebook (its C entry point takes W in/out)."""
+    import ctypes
+    lib = oracle.pixie_oracle._load()
+    W = np.ascontiguousarray(W0, np.float64).copy()
+    r0, r1 = oracle.default_radius(xd, yd)
+    f32p, f64p = ctypes.POINTER(ctypes.c_float), ctypes.POINTER(ctypes.c_double)
+    lib.oracle_som_batch(X32.ctypes.data_as(f32p), X32.shape[0], X32.shape[1], X32.shape[1],
+                         W.ctypes.data_as(f64p), xd, yd, 1, int(B), 0.05, 0.01, r0, r1)
+    return W
+
+
 def run_gpu(args):
     import torch
     import torch.distributed as dist
@@ -221,6 +420,7 @@ def run_gpu(args):
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device (no CPU fallback); use --impl reference "
                          "for the CPU arm")
+    placement = bind_to_gpu_numa_node(local)
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     distributed = world > 1
@@ -228,120 +428,55 @@ def run_gpu(args):
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=dev)
     lib = _native.lib()
-
-    # ---- resident synthetic data: this rank's 50 FOVs and their 10 % training subset
-    npx = HW * HW
-    n = NFOV * npx
-    fov_ids = list(range(rank * NFOV, (rank + 1) * NFOV))
-    X = torch.empty((n, C), dtype=torch.float32, device=dev)
-    gen_fovs_device(torch, dev, fov_ids, X)
-    ntrain_fov = int(npx * SUBSET) // 128 * 128  # tile aligned per FOV (104,832 of 104,857 rows)
-    g = torch.Generator(device=dev).manual_seed(SEED + 1000 + rank)
-    Xt = torch.empty((NFOV * ntrain_fov, C), dtype=torch.float32, device=dev)
-    for i in range(NFOV):
-        idx = torch.randperm(npx, device=dev, generator=g)[:ntrain_fov]
-        Xt[i * ntrain_fov:(i + 1) * ntrain_fov] = X[i * npx:(i + 1) * npx][idx]
-    ntrain = Xt.shape[0]
-    tile_offset = rank * (ntrain // 128)
-    # initial codebook: seeded rows of rank 0's subset, identical on every rank
-    init_idx = S.init_codebook_indices(ntrain, K, SEED)
-    W0 = Xt[torch.as_tensor(init_idx, device=dev)].to(torch.float64)
-    if distributed:
-        dist.broadcast(W0, src=0)
-    labels = torch.empty(n, dtype=torch.int32, device=dev)
-    stats = torch.zeros(S.NSTATS, dtype=torch.int64, device=dev)
     group = dist.group.WORLD if distributed else None
 
-    def step(ev=None):
-        if ev:
-            ev[0].record()
-        W = S.train_som(Xt, W0, XD, YD, rlen=1, alpha_range=(0.05, 0.01),
-                        batches_per_pass=BATCHES, group=group, tile_offset=tile_offset)
-        W32 = W.to(torch.float32)
-        if ev:
-            ev[1].record()
-        S.bmu(X, W32, labels=labels)
-        if ev:
-            ev[2].record()
-        return W32
-
-    for _ in range(max(args.warmup, 3)):
-        W32 = step()
-    torch.cuda.synchronize()
-    # parity guard inside the bench: a window of the labels against the exact fp64 kernel
-    chk = S.bmu(X[:262144], W32, flags=S.FLAG_FORCE_EXACT)
-    assert torch.equal(chk, labels[:262144]), "bench labels differ from the exact kernel"
-    S.bmu(X, W32, labels=labels, stats=stats)
-    torch.cuda.synchronize()
-    flagged_frac = float(stats[_native.STAT_ROWS_FLAGGED]) / n
-
+    # ---------------- headline: cfg2 (BASELINE.json configs[1]), resident on this rank
+    wl = Workload(torch, S, dev, rank, world, group, NFOV, HW, C, XD, YD)
+    n, ntrain = wl.n, wl.ntrain
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
-    if distributed:
-        dist.barrier()
-    torch.cuda.synchronize()
-    launches0 = lib.pixie_kernel_launches()
-    evs = [[torch.cuda.Event(enable_timing=True) for _ in range(3)] for _ in range(args.steps)]
-    t_wall0 = time.perf_counter()
-    for k in range(args.steps):
-        step(evs[k])
-    end = torch.cuda.Event(enable_timing=True)
-    end.record()
-    torch.cuda.synchronize()
-    if distributed:
-        dist.barrier()
-    wall_ms = 1e3 * (time.perf_counter() - t_wall0)
-    launches = lib.pixie_kernel_launches() - launches0
+    res = timed_steps(torch, dist, wl, args.steps, args.warmup, lib)
     # The timed region lasts only tens of milliseconds, too short for nvidia-smi's sampling
     # period: keep the SAME steps running (untimed) until the sampler has seen ~1 s of this load.
     t_clk = time.perf_counter()
     while time.perf_counter() - t_clk < 1.0:
-        step()
+        wl.step()
         torch.cuda.synchronize()
     clocks = sampler.stop() if rank == 0 else None
     if clocks is not None:
         clocks["window"] = "timed region + ~1 s of the identical step loop right behind it"
-    total_ms = evs[0][0].elapsed_time(end)
-    train_ms = sum(e[0].elapsed_time(e[1]) for e in evs)
-    assign_ms = sum(e[1].elapsed_time(e[2]) for e in evs)
-    t = torch.tensor([total_ms, train_ms, assign_ms, wall_ms], dtype=torch.float64, device=dev)
-    if distributed:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    total_ms, train_ms, assign_ms, wall_ms = [float(v) for v in t.tolist()]
-    px_step = (n + ntrain) * world
-    value = px_step * args.steps / (total_ms * 1e-3)
-
-    # ---- roofline of the dominant kernel (BMU assignment): algorithmic bytes / measured time
-    peak, peak_src = measured_peaks()
-    assign_ms_launch = assign_ms / args.steps
-    bytes_launch = n * (4 * C + 4)
-    achieved = bytes_launch / (assign_ms_launch * 1e-3) / 1e9
-    traffic = None
-    tp = os.path.join(ROOT, "profiles", "r01_assign_traffic.json")
+    oracle_err = oracle_check_sampled_shard(torch, dist, wl)
+    roofline = res.pop("roofline")
+    tp = os.path.join(ROOT, "profiles", "r02_assign_traffic.json")
+    if not os.path.exists(tp):
+        tp = os.path.join(ROOT, "profiles", "r01_assign_traffic.json")
     if os.path.exists(tp):
-        traffic = json.load(open(tp)).get("dram_bytes_per_launch")
-    roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                "frac": achieved / peak, "traffic": traffic, "kernel": "bmu_tc_kernel (assign)",
-                "bytes_per_pixel": 4 * C + 4, "pixels_per_launch": n, "peak_source": peak_src,
-                "ms_per_launch": assign_ms_launch}
+        roofline["traffic"] = json.load(open(tp)).get("dram_bytes_per_launch")
+        roofline["traffic_source"] = ("static: dram__bytes_read.sum + dram__bytes_write.sum of one "
+                                      f"ncu --set full capture, {os.path.relpath(tp, ROOT)} "
+                                      "(not measured in this run)")
+    else:
+        roofline["traffic"] = None
+    px_step = (n + ntrain) * world
+    labels_head = wl.labels[:262144].cpu().numpy()
 
     # ---- e2e: the same step through the host-buffer API (pinned host memory in, labels out)
     e2e = None
     if not args.no_e2e:
         hX = torch.empty((n, C), dtype=torch.float32).pin_memory()
-        hX.copy_(X)
+        hX.copy_(wl.X)
         hXt = torch.empty((ntrain, C), dtype=torch.float32).pin_memory()
-        hXt.copy_(Xt)
+        hXt.copy_(wl.Xt)
         hlab = torch.empty(n, dtype=torch.int32).pin_memory()
-        hXn, hXtn, hlabn = hX.numpy(), hXt.numpy(), hlab.numpy()
-        W0h = W0.cpu().numpy()
+        hXn, hlabn = hX.numpy(), hlab.numpy()
+        W0h = wl.W0.cpu().numpy()
         import ctypes
 
         def e2e_step():
             Xd = S.to_device_matrix(hXt, dev)  # H2D of the training subset
             W = S.train_som(Xd, W0h, XD, YD, rlen=1, batches_per_pass=BATCHES, group=group,
-                            tile_offset=tile_offset)
+                            tile_offset=wl.tile_offset)
             Wh = W.cpu().numpy().astype(np.float32)  # D2H of the codebook
             rc = lib.pixie_map_data_to_nodes_host_f32(
                 Wh.ctypes.data_as(ctypes.c_void_p), K, hXn.ctypes.data_as(ctypes.c_void_p), n, C,
@@ -349,7 +484,7 @@ def run_gpu(args):
             _native.check(rc, "pixie_map_data_to_nodes_host_f32")
 
         e2e_step()
-        assert np.array_equal(hlabn[:262144], labels[:262144].cpu().numpy())
+        assert np.array_equal(hlabn[:262144], labels_head)
         if distributed:
             dist.barrier()
         torch.cuda.synchronize()
@@ -358,12 +493,19 @@ def run_gpu(args):
         for _ in range(e2e_steps):
             e2e_step()
         torch.cuda.synchronize()
-        dt = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
+        mine = time.perf_counter() - t0
+        dt = torch.tensor([mine], dtype=torch.float64, device=dev)
+        lo = dt.clone()
         if distributed:
             dist.all_reduce(dt, op=dist.ReduceOp.MAX)
+            dist.all_reduce(lo, op=dist.ReduceOp.MIN)
+        h2d = int((n + ntrain) * C * 4 + K * C * 4)
         e2e = {"value": px_step * e2e_steps / float(dt), "unit": UNIT,
-               "h2d_bytes_per_step": int((n + ntrain) * C * 4 + K * C * 4),
-               "d2h_bytes_per_step": int(n * 4 + K * C * 8), "steps": e2e_steps,
+               "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": int(n * 4 + K * C * 8),
+               "steps": e2e_steps,
+               "h2d_gbs_per_rank": {"slowest": h2d * e2e_steps / float(dt) / 1e9,
+                                    "fastest": h2d * e2e_steps / float(lo) / 1e9},
+               "host_placement": placement,
                "api": "som.train_som on an uploaded pinned matrix + "
                       "pixie_map_data_to_nodes_host_f32 (pinned host rows in, host labels out)"}
         del hX, hXt, hlab
@@ -375,28 +517,55 @@ def run_gpu(args):
         oracle.build()
         cores = len(os.sched_getaffinity(0))
         nf = 4  # bounded sample: 4 of the 50 FOVs (~10-30 core-seconds)
-        Xs = X[:nf * npx].cpu().numpy()
-        px, s, tr, a = cpu_sample_run(Xs, cores)
-        cpu = {"value": px / s, "unit": UNIT, "cores": cores, "kind": "port",
-               "sample": f"{nf} of {NFOV} FOVs ({nf * npx} rows + their 10% subset): online SOM pass "
-                         f"(sequential, 1 thread) + map_data_to_nodes on {cores} threads in "
-                         f"1e6-row chunks; oracle/pixie_oracle.c (gcc -O2), {s:.1f} s",
-               "train_pixels_per_s": int(nf * npx * SUBSET) / tr,
-               "assign_pixels_per_s": nf * npx / a}
+        Xs = wl.X[:nf * wl.npx].cpu().numpy()
+        px, sec, tr, a = cpu_sample_run(Xs, cores)
+        cpu = {"value": px / sec, "unit": UNIT, "cores": cores, "kind": "port",
+               "sample": f"{nf} of {NFOV} FOVs ({nf * wl.npx} rows + their 10% subset): online SOM "
+                         f"pass (sequential, 1 thread) + map_data_to_nodes on {cores} threads in "
+                         f"1e6-row chunks; oracle/pixie_oracle.c (gcc -O2), {sec:.1f} s",
+               "train_pixels_per_s": int(nf * wl.npx * SUBSET) / tr,
+               "assign_pixels_per_s": nf * wl.npx / a,
+               "note": "train compares different algorithms (CPU: the reference's sequential online "
+                       "rule; GPU: mini-batch batch SOM); assign is like for like"}
+
+    # ---------------- second block: cfg3 (BASELINE.json configs[2]), this rank's shard
+    cfg3 = None
+    if not args.no_cfg3:
+        config2 = wl.describe("configs[1]")
+        del wl
+        torch.cuda.empty_cache()
+        w3 = Workload(torch, S, dev, rank, world, group, CFG3["nfov"], CFG3["hw"], CFG3["C"],
+                      CFG3["xd"], CFG3["yd"])
+        r3 = timed_steps(torch, dist, w3, max(2, args.steps // 2), args.warmup, lib)
+        r3["oracle_rel_err_sampled_shard"] = oracle_check_sampled_shard(torch, dist, w3)
+        r3["metric"], r3["unit"], r3["n_gpus"] = METRIC, UNIT, world
+        r3["steps"] = max(2, args.steps // 2)
+        r3["config"] = w3.describe("configs[2], per-GPU shard: 62 of its 500 FOVs")
+        r3["roofline"]["traffic"] = None
+        r3["roofline"]["note"] = ("K = 400: 2 K C / (4 C + 4) = 195 flop/byte, tensor pipe (tf32) and "
+                                  "epilogue bound, not HBM bound")
+        cfg3 = r3
+        del w3
+    else:
+        config2 = wl.describe("configs[1]")
 
     if rank == 0:
         line = {
-            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
-            "warmup": max(args.warmup, 3), "ms_per_step": total_ms / args.steps,
-            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "tf32+f32+f64",
-            "data": "synthetic", "config": workload_config(world),
-            "train_pixels_per_s": ntrain * world * args.steps / (train_ms * 1e-3),
-            "assign_pixels_per_s": n * world * args.steps / (assign_ms * 1e-3),
-            "train_ms_per_step": train_ms / args.steps, "assign_ms_per_step": assign_ms / args.steps,
-            "wall_ms_per_step": wall_ms / args.steps,
-            "rows_rechecked_frac": flagged_frac,
-            "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches),
-            "clocks": clocks,
+            "metric": METRIC, "value": res["value"], "unit": UNIT, "n_gpus": world,
+            "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": res["ms_per_step"],
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "tf32+f32+f64", "data": "synthetic", "config": config2,
+            "train_pixels_per_s": res["train_pixels_per_s"],
+            "assign_pixels_per_s": res["assign_pixels_per_s"],
+            "train_ms_per_step": res["train_ms_per_step"],
+            "assign_ms_per_step": res["assign_ms_per_step"],
+            "wall_ms_per_step": res["wall_ms_per_step"],
+            "rows_rechecked_frac": res["rows_rechecked_frac"],
+            "exchange": res["exchange"],
+            "codebooks_identical_on_all_ranks": res["codebooks_identical_on_all_ranks"],
+            "oracle_rel_err_sampled_shard": oracle_err,
+            "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e,
+            "gpu_launches": res["gpu_launches"], "clocks": clocks, "cfg3": cfg3,
         }
         _emit(line)
     if distributed:
@@ -426,6 +595,7 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-cfg3", action="store_true", help="skip the configs[2] block")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

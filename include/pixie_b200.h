@@ -161,8 +161,9 @@ int pixie_som_train_f32(const float *X, int64_t n, int32_t C, int64_t ldX, doubl
  * same time.  X is this rank's row shard, whose first row is GLOBAL tile `tile_offset` (n == 0 is
  * allowed: a rank without rows still takes part in every exchange).  The per-step statistics are
  * summed across ranks INSIDE the training kernel over NVLink peer memory (no NCCL call, no host
- * synchronisation): every CTA pushes its slice of the folded table into every rank's exchange
- * buffer, raises a per-slice flag there and adds the `world` slices it received in rank order.
+ * synchronisation): every CTA pushes the values of its slice of the folded table into every rank's
+ * exchange buffer -- value and step tag in one 16-byte store, so the receiver only polls its own
+ * memory -- and adds the `world` values of each element in rank order.
  * `peer_bufs` is a HOST array of `world` device pointers, entry r being rank r's exchange buffer
  * mapped into this process (CUDA IPC / symmetric memory), each at least
  * pixie_peer_buffer_bytes(C, K) bytes, zero-initialised once.  `flag_base` must grow by at least
