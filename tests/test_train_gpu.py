@@ -140,3 +140,56 @@ def test_online_som_through_the_pyflowsom_shaped_call():
     assert np.array_equal(auto, S.som(big, xdim=4, ydim=5, rlen=1, seed=11, algorithm="batch"))
     with pytest.raises(ValueError):
         S.som(X, xdim=4, ydim=5, algorithm="nope")
+
+
+# ------------------------------------------------------------------------------------------------
+# the BASELINE shapes that used to fall off the whole-pass kernel (round 1: step-by-step path)
+# ------------------------------------------------------------------------------------------------
+def test_train_matches_oracle_cfg4_shape():
+    """cfg4's shape: 100 features, 10 x 10 SOM (group tables in global memory, red.v4 accumulate)."""
+    n, C, xd, yd = 128 * 400 + 37, 100, 10, 10
+    X = pixie_like(n, C, seed=5)
+    idx = oracle.init_codebook_indices(n, xd * yd, 42)
+    ref = oracle.som_batch(X, xd, yd, rlen=1, init_idx=idx)
+    Xd = S.to_device_matrix(X)
+    W = S.train_som(Xd, X[idx].astype(np.float64), xd, yd, rlen=1).cpu().numpy()
+    assert rel_err(W, ref) < RTOL
+    W2 = S.train_som(Xd, X[idx].astype(np.float64), xd, yd, rlen=1).cpu().numpy()
+    np.testing.assert_array_equal(W, W2)  # red.global.add in a fixed order: still deterministic
+
+
+def test_train_matches_oracle_cfg3_shape_global_tables_forced_shared_shape():
+    """40 channels, 20 x 20 SOM: every node class, both accumulate forms (shared-memory tables are
+    forced for a shape that fits them through PIXIE_TAB_GLOBAL in test_table_kinds below)."""
+    n, C, xd, yd = 128 * 300 + 5, 40, 20, 20
+    X = pixie_like(n, C, seed=6)
+    idx = oracle.init_codebook_indices(n, xd * yd, 42)
+    ref = oracle.som_batch(X, xd, yd, rlen=2, init_idx=idx)
+    W = S.train_som(S.to_device_matrix(X), X[idx].astype(np.float64), xd, yd, rlen=2).cpu().numpy()
+    assert rel_err(W, ref) < RTOL
+
+
+@pytest.mark.parametrize("tab_global", ["0", "1"])
+def test_table_kinds_agree(tab_global, monkeypatch):
+    """Shared-memory and global group tables (PIXIE_TAB_GLOBAL forces either for a shape that fits
+    both) give the oracle's codebook; the two differ only in fp32 summation order."""
+    monkeypatch.setenv("PIXIE_TAB_GLOBAL", tab_global)
+    n, C, xd, yd = 128 * 200 + 64, 24, 8, 8
+    X = pixie_like(n, C, seed=9)
+    idx = oracle.init_codebook_indices(n, xd * yd, 3)
+    ref = oracle.som_batch(X, xd, yd, rlen=1, init_idx=idx)
+    W = S.train_som(S.to_device_matrix(X), X[idx].astype(np.float64), xd, yd, rlen=1).cpu().numpy()
+    assert rel_err(W, ref) < RTOL
+
+
+def test_train_matches_oracle_cfg2_full_size():
+    """cfg2's real training size: 5,241,600 rows x 32 channels, 10 x 10 SOM, one pass of 32
+    mini-batches (the fp64 oracle takes ~20 s)."""
+    n, C = 5241600, 32
+    base = pixie_like(1 << 18, C, seed=12)
+    X = np.ascontiguousarray(np.tile(base, (20, 1))[:n])
+    X *= (1.0 + 1e-3 * np.random.default_rng(1).random((n, 1), dtype=np.float32))  # no exact repeats
+    idx = oracle.init_codebook_indices(n, 100, 42)
+    ref = oracle.som_batch(X, 10, 10, rlen=1, init_idx=idx)
+    W = S.train_som(S.to_device_matrix(X), X[idx].astype(np.float64), 10, 10, rlen=1).cpu().numpy()
+    assert rel_err(W, ref) < RTOL
