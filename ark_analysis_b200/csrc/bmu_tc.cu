@@ -26,6 +26,7 @@
 // NG = 4 with 56-column slices (<= 112 registers/thread) for K <= 128, NG = 2 with wider slices
 // above that.  The epilogue is instruction-latency bound, so warps per scheduler matter.
 #include <float.h>
+#include <stdio.h>
 #include <stdlib.h>
 
 #include "bmu_tc_kernel.cuh"
@@ -48,6 +49,9 @@ const Variant kVariants[] = {
     {32, 1, 1, 2}, {32, 2, 1, 2}, {48, 2, 1, 2}, {50, 2, 1, 2}, {56, 2, 1, 2}, {64, 2, 1, 2},
     {80, 2, 1, 2}, {100, 2, 1, 2}, {104, 2, 1, 2}, {128, 2, 1, 2},
     {80, 2, 2, 2}, {100, 2, 2, 2}, {104, 2, 2, 2}, {128, 2, 2, 2},
+    // ({40,52,64}, 2, 4, 4) -- four chunks per tile through ONE buffer per group, four groups for
+    // K up to 512 -- exist in the kernel template, are bit-exact, and were measured 4-8 % SLOWER than
+    // the two-group variants (profiles/r02_notes.md): not instantiated.
 };
 }  // namespace
 
@@ -63,8 +67,14 @@ TcPlan make_tc_plan(int C, int K, bool acc)
     best.ok = false;
     if (C < 1 || C > 128 || K < 1 || K > 512) return best;
     const int cap_stages = env_int("PIXIE_TC_STAGES", kMaxStages);
+    // experiments: PIXIE_TC_VARIANT=SL,SPC,NCH,NG restricts the choice to one variant
+    int only[4] = {0, 0, 0, 0};
+    if (const char *ov = getenv("PIXIE_TC_VARIANT"))
+        if (sscanf(ov, "%d,%d,%d,%d", &only[0], &only[1], &only[2], &only[3]) != 4) only[0] = 0;
     long best_cost = -1;
     for (const Variant &v : kVariants) {
+        if (only[0] && (v.SL != only[0] || v.spc != only[1] || v.NCH != only[2] || v.NG != only[3]))
+            continue;
         TcPlan p{};
         p.C = C;
         p.K = K;
@@ -81,7 +91,7 @@ TcPlan make_tc_plan(int C, int K, bool acc)
         p.Nmma = (p.Nchunk + 15) / 16 * 16;
         p.Ntot = (v.NCH - 1) * p.Nchunk + p.Nmma;
         if (p.Nchunk * v.NCH < K) continue;
-        p.nbuf = v.NCH == 1 ? v.NG : 2;
+        p.nbuf = v.NCH == 2 ? 2 : v.NG;
         const int need = p.nbuf * p.Nmma;
         if (need > 512) continue;
         p.tmem_cols = 32;
@@ -151,8 +161,10 @@ TcPlan make_tc_plan(int C, int K, bool acc)
         p.acc = acc ? 1 : 0;
         p.smem_bytes = p.off_acc + acc_bytes + 1024u;
         p.ok = true;
-        // fewest padded codebook rows first; then more epilogue groups; then deeper pipeline
-        const long cost = (long)(p.Nchunk * v.NCH) * 1000 - v.NG * 10 - p.nstage + (p.tab_global ? 15 : 0);
+        // fewest padded codebook rows first; then more epilogue groups; then tables on chip and a
+        // deeper pipeline
+        const long cost = (long)(p.Nchunk * v.NCH) * 1000 - v.NG * 10 - p.nstage +
+                          (p.tab_global ? 15 : 0);
         if (best_cost < 0 || cost < best_cost) {
             best_cost = cost;
             best = p;

@@ -730,8 +730,12 @@ bmu_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ T
     static_assert(NCH == 1 || NCHUNK % 8 == 0, "chunk base must stay on a swizzle-atom row");
     constexpr int NS = SPC * NCH;           // slices per tile
     constexpr int NW = (SL + 31) / 32;      // mask words per slice
-    constexpr int NBUF = NCH == 1 ? NG : 2; // TMEM accumulator buffers
-    static_assert(NCH == 1 || NG == 2, "two chunks per tile only with two epilogue groups");
+    // TMEM accumulator buffers: one per epilogue group (NCH = 1: the tile's only chunk; NCH = 4:
+    // the tile's chunks go through it one after the other), or two shared by the two groups
+    // (NCH = 2: both chunks of a tile in flight at once)
+    constexpr int NBUF = NCH == 2 ? 2 : NG;
+    static_assert(NCH == 1 || NCH == 2 || NCH == 4, "accumulator chunks per tile");
+    static_assert(NCH != 2 || NG == 2, "two chunks per tile only with two epilogue groups");
 
     extern __shared__ uint8_t smem_raw[];
     const TcPlan &pl = p.plan;
@@ -873,21 +877,9 @@ bmu_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ T
             const uint32_t wblk_bytes = (uint32_t)((NCH - 1) * NCHUNK + NMMA) * 128u;
             if constexpr (ACC) load_image();  // this step's codebook (the producer warp is busy ahead)
             mbar_wait(bar_w, (uint32_t)st & 1u);
-            uint32_t s = base_seq % (uint32_t)nstage;
-            uint32_t ph = (base_seq / (uint32_t)nstage) & 1u;
-            for (uint32_t it = 0; it < cnt; ++it, ph ^= (++s == (uint32_t)nstage), s = s == (uint32_t)nstage ? 0u : s) {
-                const uint32_t seq = base_seq + it;
-                mbar_wait(bar_full + 8u * s, ph);
-                PIXIE_TRACE(1, seq);
-                const uint32_t xs_addr = sbase + pl.off_x + s * pl.stage_bytes;
-#pragma unroll
-                for (int c = 0; c < NCH; ++c) {
-                    const uint32_t q = seq * (uint32_t)NCH + (uint32_t)c;  // accumulator-chunk counter
-                    const uint32_t buf = q % NBUF;
-                    const uint32_t bph = (q / NBUF) & 1u;
-                    mbar_wait(bar_tempty + 8u * buf, bph ^ 1u);
-                    tc_fence_after();
-                    if (elect_one()) {
+            // the MMAs of one accumulator chunk (all K-steps + the bias K-step) and their commit
+            auto issue_chunk = [&](uint32_t xs_addr, int c, uint32_t buf) {
+                if (elect_one()) {
                     const uint32_t d_tmem = tmem_base + buf * (uint32_t)NMMA;
                     const uint32_t wrow = (uint32_t)(c * NCHUNK) * 128u;
                     for (int ks = 0; ks < pl.ksteps; ++ks) {
@@ -900,9 +892,49 @@ bmu_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ T
                         sbase + pl.off_bias + (uint32_t)(c * NCHUNK / 8) * 256u, 128u, 256u);
                     mma_tf32(d_tmem, desc_ones, dbias, idesc, 1u);
                     mma_commit(bar_tfull + 8u * buf);
+                }
+                __syncwarp();
+            };
+            if constexpr (NCH <= 2) {
+                uint32_t s = base_seq % (uint32_t)nstage;
+                uint32_t ph = (base_seq / (uint32_t)nstage) & 1u;
+                for (uint32_t it = 0; it < cnt; ++it, ph ^= (++s == (uint32_t)nstage), s = s == (uint32_t)nstage ? 0u : s) {
+                    const uint32_t seq = base_seq + it;
+                    mbar_wait(bar_full + 8u * s, ph);
+                    PIXIE_TRACE(1, seq);
+                    const uint32_t xs_addr = sbase + pl.off_x + s * pl.stage_bytes;
+#pragma unroll
+                    for (int c = 0; c < NCH; ++c) {
+                        const uint32_t q = seq * (uint32_t)NCH + (uint32_t)c;  // accumulator-chunk counter
+                        const uint32_t buf = q % NBUF;
+                        const uint32_t bph = (q / NBUF) & 1u;
+                        mbar_wait(bar_tempty + 8u * buf, bph ^ 1u);
+                        tc_fence_after();
+                        issue_chunk(xs_addr, c, buf);
+                        PIXIE_TRACE(2, seq);
                     }
-                    __syncwarp();
-                    PIXIE_TRACE(2, seq);
+                }
+            } else {
+                // Four chunks per tile through the group's ONE buffer: chunk c + 1 can only be
+                // issued once the group has drained chunk c.  Issuing tile by tile would stall the
+                // tensor pipe on every drain, so the tiles go in rounds of NG (one per group) and
+                // the round is walked chunk-major: while group g drains chunk c, chunk c of the
+                // other groups' tiles is issued.
+                for (uint32_t it0 = 0; it0 < cnt; it0 += (uint32_t)NG) {
+                    const uint32_t nt = cnt - it0 < (uint32_t)NG ? cnt - it0 : (uint32_t)NG;
+#pragma unroll 1
+                    for (int c = 0; c < NCH; ++c) {
+                        for (uint32_t t = 0; t < nt; ++t) {
+                            const uint32_t seq = base_seq + it0 + t;
+                            const uint32_t s = seq % (uint32_t)nstage;
+                            const uint32_t g = seq % (uint32_t)NG, use = seq / (uint32_t)NG;
+                            if (c == 0) mbar_wait(bar_full + 8u * s, (seq / (uint32_t)nstage) & 1u);
+                            const uint32_t q = use * (uint32_t)NCH + (uint32_t)c;  // per-group chunk counter
+                            mbar_wait(bar_tempty + 8u * g, (q & 1u) ^ 1u);
+                            tc_fence_after();
+                            issue_chunk(sbase + pl.off_x + s * pl.stage_bytes, c, g);
+                        }
+                    }
                 }
             }
         }
@@ -1004,9 +1036,10 @@ bmu_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ T
 #pragma unroll
             for (int c = 0; c < NCH; ++c) {
                 uint32_t buf, bph;
-                if constexpr (NCH == 1) {
+                if constexpr (NCH != 2) {
+                    // the group's own buffer; its uses are numbered use * NCH + c
                     buf = (uint32_t)g;
-                    bph = use & 1u;
+                    bph = (use * (uint32_t)NCH + (uint32_t)c) & 1u;
                 } else {
                     // chunk counter q = seq * 2 + c; buffers alternate
                     const uint32_t q = seq * 2u + (uint32_t)c;
