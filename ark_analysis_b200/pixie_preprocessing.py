@@ -161,7 +161,8 @@ def load_fov_channels(tiff_dir, fov, channels, img_sub_folder=None):
 
 def preprocess_fov(base_dir, tiff_dir, data_dir, subset_dir, seg_dir, seg_suffix,
                    img_sub_folder, is_mibitiff, channels, blur_factor,
-                   subset_proportion, pixel_thresh_val, seed, channel_norm_df, fov):
+                   subset_proportion, pixel_thresh_val, seed, channel_norm_df, fov,
+                   _device_result=None):
     """The reference's ``preprocess_fov`` (pixie_preprocessing.py:83-185): load one FOV's channel
     images (and its segmentation mask), normalise by ``channel_norm_df``, blur / filter / row-
     normalise, write the full table to ``base_dir/data_dir/<fov>.feather`` and the sampled subset to
@@ -185,7 +186,182 @@ def preprocess_fov(base_dir, tiff_dir, data_dir, subset_dir, seg_dir, seg_suffix
                              compression='uncompressed')
     io_utils.write_dataframe(pixel_mat_subset, os.path.join(base_dir, subset_dir, fov + ".feather"),
                              compression='uncompressed')
+    if _device_result is not None:  # create_pixel_matrix takes the quantiles from the device rows
+        _device_result.update(res)
     return pixel_mat
+
+
+# ------------------------------------------------------------------------------------------------
+# the cohort driver (reference pixie_preprocessing.py:188-456) and its raw-image statistics
+# (pixel_cluster_utils.py:16-108)
+# ------------------------------------------------------------------------------------------------
+def calculate_channel_percentiles(tiff_dir, fovs, channels, img_sub_folder, percentile):
+    """1 x C DataFrame: per channel, the mean over FOVs of ``np.quantile(img[img > 0], percentile)``
+    (FOVs without a non-zero pixel are left out), columns in natural order -- the reference's
+    ``calculate_channel_percentiles``.  Host numpy on the raw images: image IO bound, one scalar per
+    (FOV, channel)."""
+    import pandas as pd
+    means = []
+    for channel in channels:
+        per_fov = []
+        for fov in fovs:
+            img = load_fov_channels(tiff_dir, fov, [channel], img_sub_folder)[:, :, 0]
+            nz = img[img > 0]
+            if len(nz) > 0:
+                per_fov.append(np.quantile(nz, percentile))
+        means.append(np.mean(per_fov))
+    order = sorted(range(len(channels)), key=lambda i: natural_key(channels[i]))
+    return pd.DataFrame([[means[i] for i in order]], columns=[channels[i] for i in order])
+
+
+def calculate_pixel_intensity_percentile(tiff_dir, fovs, channels, img_sub_folder,
+                                         channel_percentiles, percentile=0.05):
+    """Mean over FOVs of the ``percentile`` quantile of the per-pixel total signal after every
+    channel was divided by its ``channel_percentiles`` value (the reference's function of the
+    same name): the pixel threshold of the preprocessing."""
+    norm_vect = channel_percentiles.iloc[0].values.reshape([1, 1, -1])
+    per_fov = []
+    for fov in fovs:
+        img = load_fov_channels(tiff_dir, fov, channels, img_sub_folder)
+        per_fov.append(np.quantile(np.sum(img / norm_vect, axis=-1), percentile))
+    return np.mean(per_fov)
+
+
+def check_for_modified_channels(tiff_dir, test_fov, img_sub_folder, channels):
+    """Warn when a selected channel also exists in a modified version (``_smoothed``,
+    ``_nuc_include``, ``_nuc_exclude``) in the example FOV's folder."""
+    import os
+    import warnings
+    present = set(io_utils.remove_file_extensions(
+        io_utils.list_files(os.path.join(tiff_dir, test_fov, img_sub_folder or ''))))
+    for channel in channels:
+        for mod in ('_smoothed', '_nuc_include', '_nuc_exclude'):
+            if channel + mod in present:
+                warnings.warn('You selected {} as the channel to analyze, but there were potential'
+                              ' modified channels found: {}. Make sure you selected the correct '
+                              'version of the channel for inclusion in '
+                              'clustering'.format(channel, channel + mod))
+
+
+class _Cohort:
+    """Files and restart state of one preprocessing run under ``base_dir``."""
+
+    def __init__(self, base_dir, pixel_output_dir, data_dir, subset_dir, pre_name, thresh_name):
+        import os
+        self.data = os.path.join(base_dir, data_dir)
+        self.subset = os.path.join(base_dir, subset_dir)
+        self.pre_norm = os.path.join(base_dir, pixel_output_dir, pre_name)
+        self.thresh = os.path.join(base_dir, pixel_output_dir, thresh_name)
+        self.quantiles = os.path.join(self.data, "channel_norm_post_rownorm_perfov.csv")
+        for d in (self.data, self.subset):
+            if not os.path.exists(d):
+                os.mkdir(d)
+
+    def reset_if_channels_changed(self, channels):
+        """A different channel set invalidates everything written so far."""
+        import os
+        from shutil import rmtree
+        if not os.path.exists(self.pre_norm):
+            return
+        if set(io_utils.read_dataframe(self.pre_norm).columns.values) == set(channels):
+            return
+        print("New channels provided: overwriting whole cohort")
+        for d in (self.data, self.subset):
+            rmtree(d)
+            os.mkdir(d)
+        os.remove(self.pre_norm)
+        os.remove(self.thresh)
+
+    def finished_fovs(self):
+        """FOVs with BOTH their full and their subset file (a lone file is regenerated)."""
+        both = set(io_utils.list_files(self.subset, substrs='.feather')) & \
+            set(io_utils.list_files(self.data, substrs='.feather'))
+        return set(io_utils.remove_file_extensions(sorted(both)))
+
+
+def create_pixel_matrix(fovs, channels, base_dir, tiff_dir, seg_dir,
+                        img_sub_folder="TIFs", seg_suffix='_whole_cell.tiff',
+                        pixel_output_dir='pixel_output_dir',
+                        data_dir='pixel_mat_data',
+                        subset_dir='pixel_mat_subsetted',
+                        norm_vals_name_pre_rownorm='channel_norm_pre_rownorm.feather',
+                        norm_vals_name_post_rownorm='channel_norm_post_rownorm.feather',
+                        pixel_thresh_name='pixel_thresh.feather',
+                        channel_percentile_pre_rownorm=0.99, channel_percentile_post_rownorm=0.999,
+                        is_mibitiff=False, blur_factor=2, subset_proportion=0.1, seed=42,
+                        multiprocess=False, batch_size=5):
+    """The notebook-facing driver of the preprocessing (reference pixie_preprocessing.py:188-456):
+    per FOV, blur / threshold / row-normalise the channel images on the device
+    (``preprocess_fov``), write the full and the subsetted pixel tables, and collect the per-FOV
+    99.9 % quantiles whose mean becomes ``base_dir/norm_vals_name_post_rownorm`` -- the row
+    ``PixelSOMCluster`` divides by.  Same arguments, files, restart behaviour and messages as the
+    reference.  ``multiprocess`` / ``batch_size`` are accepted for compatibility: the FOVs go
+    through the one GPU in turn (a FOV takes ~1 ms of kernels; the loop is image-IO bound)."""
+    import os
+    import pandas as pd
+
+    channels.sort(key=natural_key)
+    if subset_proportion <= 0 or subset_proportion > 1:
+        raise ValueError('Invalid subset percentage entered: must be in (0, 1]')
+    io_utils.validate_paths([base_dir, tiff_dir, os.path.join(base_dir, pixel_output_dir)])
+
+    cohort = _Cohort(base_dir, pixel_output_dir, data_dir, subset_dir,
+                     norm_vals_name_pre_rownorm, pixel_thresh_name)
+    cohort.reset_if_channels_changed(channels)
+
+    todo = set(fovs) - cohort.finished_fovs()
+    if not todo:
+        print("There are no more FOVs to preprocess, skipping")
+        return
+    # FOVs whose quantiles never reached the per-FOV file are redone as well
+    quant_all = pd.read_csv(cohort.quantiles, index_col="channel") \
+        if os.path.exists(cohort.quantiles) else pd.DataFrame()
+    todo |= set(fovs) - set(quant_all.columns)
+    todo = sorted(todo, key=natural_key)
+    if len(todo) < len(fovs):
+        print("Restarting preprocessing from FOV %s, "
+              "%d fovs left to process" % (todo[0], len(todo)))
+
+    check_for_modified_channels(tiff_dir=tiff_dir, test_fov=fovs[0],
+                                img_sub_folder=img_sub_folder, channels=channels)
+
+    # cohort-wide statistics of the raw images: computed once, then read back on a restart
+    if os.path.exists(cohort.pre_norm):
+        pre_norm = io_utils.read_dataframe(cohort.pre_norm)
+    else:
+        pre_norm = calculate_channel_percentiles(tiff_dir, fovs, channels, img_sub_folder,
+                                                 channel_percentile_pre_rownorm)
+        io_utils.write_dataframe(pre_norm, cohort.pre_norm, compression='uncompressed')
+    if os.path.exists(cohort.thresh):
+        pixel_thresh_val = io_utils.read_dataframe(cohort.thresh)['pixel_thresh_val'].values[0]
+    else:
+        pixel_thresh_val = calculate_pixel_intensity_percentile(
+            tiff_dir, fovs, channels, img_sub_folder, pre_norm)
+        io_utils.write_dataframe(pd.DataFrame({'pixel_thresh_val': [pixel_thresh_val]}),
+                                 cohort.thresh, compression='uncompressed')
+
+    for done, fov in enumerate(todo, start=1):
+        on_device = {}
+        preprocess_fov(base_dir, tiff_dir, data_dir, subset_dir, seg_dir, seg_suffix,
+                       img_sub_folder, is_mibitiff, channels, blur_factor, subset_proportion,
+                       pixel_thresh_val, seed, pre_norm, fov, _device_result=on_device)
+        # the FOV's quantiles of the non-zero entries, from the rows still on the device
+        quant_fov = fov_channel_quantiles(on_device["X64"], channels,
+                                          channel_percentile_post_rownorm, name=fov)
+        quant_fov.index.name = "channel"
+        quant_all = quant_all.merge(quant_fov, how="outer", left_index=True, right_index=True)
+        quant_all.to_csv(cohort.quantiles)  # after every FOV: the restart point
+        if multiprocess:
+            if done % batch_size == 0 or done == len(todo):
+                print("Processed %d fovs" % done)
+        elif done % 10 == 0 or done == len(todo):
+            print("Processed %d fovs" % done)
+
+    mean_quant = pd.DataFrame(quant_all.mean(axis=1))
+    mean_quant = mean_quant.loc[sorted(mean_quant.index, key=natural_key)]
+    io_utils.write_dataframe(mean_quant.T, os.path.join(base_dir, norm_vals_name_post_rownorm),
+                             compression='uncompressed')
+    os.remove(cohort.quantiles)
 
 
 # ------------------------------------------------------------------------------------------------

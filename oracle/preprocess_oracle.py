@@ -141,3 +141,53 @@ def preprocess_fov(base_dir, tiff_dir, data_dir, subset_dir, seg_dir, seg_suffix
     paf.write_feather(sub_mat, os.path.join(base_dir, subset_dir, fov + ".feather"),
                       compression='uncompressed')
     return mat
+
+
+def create_pixel_matrix(fovs, channels, base_dir, tiff_dir, seg_dir, img_sub_folder="TIFs",
+                        seg_suffix='_whole_cell.tiff', pixel_output_dir='pixel_output_dir',
+                        data_dir='pixel_mat_data', subset_dir='pixel_mat_subsetted',
+                        norm_vals_name_post_rownorm='channel_norm_post_rownorm.feather',
+                        channel_percentile_pre_rownorm=0.99, channel_percentile_post_rownorm=0.999,
+                        blur_factor=2, subset_proportion=0.1, seed=42):
+    """The arithmetic of pixie_preprocessing.py:188-456 for a fresh cohort (no restart logic),
+    with numpy / pandas / scipy only: raw-image channel percentiles (pixel_cluster_utils.py:16-57),
+    the pixel threshold (:60-108), preprocess_fov per FOV, the per-FOV 99.9 % quantiles of the
+    non-zero entries and their mean.  Returns (pre_norm_df, pixel_thresh_val, post_norm_df)."""
+    import os
+
+    import pandas as pd
+    import pyarrow.feather as paf
+    from PIL import Image
+
+    def load(fov, chans):
+        sub = os.path.join(tiff_dir, fov, img_sub_folder) if img_sub_folder else os.path.join(tiff_dir, fov)
+        return np.stack([np.asarray(Image.open(os.path.join(sub, c + '.tiff'))) for c in chans], -1)
+
+    channels = sorted(channels)
+    means = []
+    for ch in channels:
+        vals = []
+        for fov in fovs:
+            img = load(fov, [ch])[:, :, 0]
+            img = img[img > 0]
+            if len(img) > 0:
+                vals.append(np.quantile(img, channel_percentile_pre_rownorm))
+        means.append(np.mean(vals))
+    pre = pd.DataFrame(np.expand_dims(means, axis=0), columns=channels)
+    norm_vect = pre.iloc[0].values.reshape([1, 1, -1])
+    thresh = np.mean([np.quantile(np.sum(load(f, channels) / norm_vect, axis=-1), 0.05) for f in fovs])
+    for d in (data_dir, subset_dir):
+        os.makedirs(os.path.join(base_dir, d), exist_ok=True)
+    quant = pd.DataFrame()
+    drop = ['fov', 'row_index', 'column_index'] + (['label'] if seg_dir else [])
+    for fov in fovs:
+        mat = preprocess_fov(base_dir, tiff_dir, data_dir, subset_dir, seg_dir, seg_suffix,
+                             img_sub_folder, list(channels), blur_factor, subset_proportion, thresh,
+                             seed, pre, fov)
+        q = mat.drop(columns=drop).replace(0, np.nan).quantile(
+            q=channel_percentile_post_rownorm, axis=0).rename(fov)
+        q.index.name = "channel"
+        quant = quant.merge(q, how="outer", left_index=True, right_index=True)
+    post = pd.DataFrame(quant.mean(axis=1)).sort_index().T
+    paf.write_feather(post, os.path.join(base_dir, norm_vals_name_post_rownorm), compression='uncompressed')
+    return pre, thresh, post

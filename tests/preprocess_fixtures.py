@@ -10,7 +10,7 @@ from PIL import Image
 
 
 def make_tree(temp_dir, rng, fovs=('fov0', 'fov1'), chans=('chan0', 'chan1', 'chan2'),
-              shape=(40, 36), sub_dir='TIFs'):
+              shape=(40, 36), sub_dir='TIFs', dtype=np.float32):
     tiff_dir = os.path.join(temp_dir, 'sample_image_data')
     seg_dir = os.path.join(temp_dir, 'segmentation')
     os.mkdir(tiff_dir)
@@ -19,7 +19,7 @@ def make_tree(temp_dir, rng, fovs=('fov0', 'fov1'), chans=('chan0', 'chan1', 'ch
         d = os.path.join(tiff_dir, fov, sub_dir) if sub_dir else os.path.join(tiff_dir, fov)
         os.makedirs(d)
         for ch in chans:
-            plane = rng.gamma(0.8, 20.0, shape).astype(np.float32)
+            plane = rng.gamma(0.8, 20.0, shape).astype(dtype)
             Image.fromarray(plane).save(os.path.join(d, ch + '.tiff'))
         Image.fromarray(rng.integers(0, 16, shape).astype(np.int32)).save(
             os.path.join(seg_dir, fov + '_whole_cell.tiff'))

@@ -348,3 +348,18 @@ def test_concurrent_host_threads_share_nothing():
     for t in threads:
         t.join()
     assert not errors, errors[:5]
+
+
+def test_torch_library_ops():
+    """torch.ops.pixie_b200.* are the same kernels behind torch.library custom ops."""
+    import ark_analysis_b200.torch_ops  # noqa: F401  (registers the ops)
+    X = pixie_like(128 * 20 + 3, 16, seed=4)
+    W = X[:25].copy()
+    Xd, Wd = S.to_device_matrix(X), torch.from_numpy(W).cuda()
+    lab = torch.ops.pixie_b200.bmu(Xd, Wd)
+    np.testing.assert_array_equal(lab.cpu().numpy(), oracle.map_data_to_nodes_f32(W, X)[0])
+    lab2, SN = torch.ops.pixie_b200.bmu_sums(Xd, Wd)
+    assert torch.equal(lab, lab2) and float(SN[:, -1].sum()) == X.shape[0]
+    W64 = torch.ops.pixie_b200.som_train(Xd, Wd.double(), 5, 5, 1, 0.05, 0.01, 0)
+    ref = oracle.som_batch(X, 5, 5, rlen=1, init_idx=np.arange(25))
+    assert np.abs(W64.cpu().numpy() - ref).max() / np.abs(ref).max() < 1e-4

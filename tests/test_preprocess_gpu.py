@@ -7,6 +7,7 @@ import numpy as np
 import pandas as pd
 import pytest
 import torch
+import pyarrow.feather as paf
 from scipy import ndimage
 
 from oracle import preprocess_oracle as PO
@@ -149,3 +150,51 @@ def test_preprocess_fov_writes_the_reference_files(with_seg, sub_dir, rng, tmp_p
     pd.testing.assert_frame_equal(m_sub, o_sub)
     pd.testing.assert_frame_equal(m_ret, o_ret)
     assert 0 < len(m_full) < 40 * 36
+
+
+def test_create_pixel_matrix_matches_the_reference_route(tmp_path, rng, capsys):
+    """The cohort driver end to end: raw-image statistics, per-FOV tables, the post-row-norm
+    normalisation row -- every file equal to the numpy / scipy / pandas route's; then the restart
+    and the channel-change behaviours of the reference (pixie_preprocessing.py:260-300)."""
+    import preprocess_fixtures as PF
+    fovs, chans = ['fov0', 'fov1'], ['chan0', 'chan1', 'chan2']
+    # integer-typed images (the usual TIFFs): the raw-image quantiles, hence the normalisation row,
+    # are float64 and the reference's arithmetic is float64 throughout -- the case mirrored bit for
+    # bit.  (float32 images make numpy keep the whole reference pipeline in float32; the mirror
+    # stays in fp64 and then agrees to ~1e-6 relative: DESIGN.md section 5.2.)
+    tiff_dir, seg_dir, _ = PF.make_tree(str(tmp_path), rng, dtype=np.uint16)
+    bases = {}
+    for tag in ('mirror', 'oracle'):
+        base = os.path.join(str(tmp_path), tag)
+        os.makedirs(os.path.join(base, 'pixel_output_dir'))
+        bases[tag] = base
+    PP.create_pixel_matrix(list(fovs), list(chans), bases['mirror'], tiff_dir, seg_dir)
+    assert "Processed 2 fovs" in capsys.readouterr().out
+    pre, thresh, post = PO.create_pixel_matrix(list(fovs), list(chans), bases['oracle'], tiff_dir, seg_dir)
+    m, o = bases['mirror'], bases['oracle']
+    pd.testing.assert_frame_equal(
+        paf.read_feather(os.path.join(m, 'pixel_output_dir', 'channel_norm_pre_rownorm.feather')), pre)
+    got_thresh = paf.read_feather(os.path.join(m, 'pixel_output_dir', 'pixel_thresh.feather'))
+    assert got_thresh['pixel_thresh_val'].values[0] == thresh
+    pd.testing.assert_frame_equal(
+        paf.read_feather(os.path.join(m, 'channel_norm_post_rownorm.feather')),
+        paf.read_feather(os.path.join(o, 'channel_norm_post_rownorm.feather')))
+    for fov in fovs:
+        for d in ('pixel_mat_data', 'pixel_mat_subsetted'):
+            pd.testing.assert_frame_equal(paf.read_feather(os.path.join(m, d, fov + '.feather')),
+                                          paf.read_feather(os.path.join(o, d, fov + '.feather')))
+    assert not os.path.exists(os.path.join(m, 'pixel_mat_data', 'channel_norm_post_rownorm_perfov.csv'))
+    # everything is there: a second call does nothing
+    PP.create_pixel_matrix(list(fovs), list(chans), m, tiff_dir, seg_dir)
+    assert "There are no more FOVs to preprocess, skipping" in capsys.readouterr().out
+    # a lost subset file: only that FOV is redone
+    os.remove(os.path.join(m, 'pixel_mat_subsetted', 'fov1.feather'))
+    PP.create_pixel_matrix(list(fovs), list(chans), m, tiff_dir, seg_dir)
+    assert os.path.exists(os.path.join(m, 'pixel_mat_subsetted', 'fov1.feather'))
+    # other channels: the cohort starts over
+    PP.create_pixel_matrix(list(fovs), ['chan0', 'chan1'], m, tiff_dir, seg_dir)
+    assert "New channels provided: overwriting whole cohort" in capsys.readouterr().out
+    assert list(paf.read_feather(os.path.join(m, 'channel_norm_post_rownorm.feather')).columns) == \
+        ['chan0', 'chan1']
+    with pytest.raises(ValueError):
+        PP.create_pixel_matrix(list(fovs), list(chans), m, tiff_dir, seg_dir, subset_proportion=0)
