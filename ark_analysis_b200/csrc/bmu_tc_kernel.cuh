@@ -824,7 +824,12 @@ bmu_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ T
     };
     // X tiles of one step -> stages.  The whole warp walks the loop (warp-uniform control flow);
     // one elected lane issues.
-    auto produce_step = [&](const StepTiles &stp, uint32_t cnt, uint32_t seq0, int st) {
+    // Tile it + nstage -- the next occupant of the stage being filled -- is prefetched into L2 at
+    // the same time (past the step's last tile: the first tiles of the next step, `nxt`).  Worth
+    // 2 % where the pipeline is shallow (K = 400, C = 40: three stages), nothing elsewhere
+    // (profiles/r02_notes.md section 8); PIXIE_DBG_FLAGS=8 switches it off for A/B runs.
+    auto produce_step = [&](const StepTiles &stp, uint32_t cnt, uint32_t seq0, int st,
+                            const StepTiles &nxt, uint32_t nxt_cnt) {
         uint32_t s = seq0 % (uint32_t)nstage;          // one division per step, then
         uint32_t ph = (seq0 / (uint32_t)nstage) & 1u;  // incremental
         for (uint32_t it = 0; it < cnt; ++it, ph ^= (++s == (uint32_t)nstage), s = s == (uint32_t)nstage ? 0u : s) {
@@ -832,11 +837,23 @@ bmu_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ T
             const int64_t j = (int64_t)blockIdx.x + (int64_t)it * gridDim.x;
             const int64_t tile = stp.first + j * stp.stride;
             const int32_t row0 = (int32_t)(tile * kTile);
+            const uint32_t ita = it + (uint32_t)nstage;
+            int64_t ptile = -1;
+            if (!(p.dbg_flags & 8)) {
+                if (ita < cnt)
+                    ptile = stp.first + ((int64_t)blockIdx.x + (int64_t)ita * gridDim.x) * stp.stride;
+                else if (ita - cnt < nxt_cnt)
+                    ptile = nxt.first +
+                            ((int64_t)blockIdx.x + (int64_t)(ita - cnt) * gridDim.x) * nxt.stride;
+            }
             if (elect_one()) {
                 mbar_arrive_expect_tx(bar_full + 8u * s, pl.stage_bytes);
                 for (int b = 0; b < pl.nblkX; ++b)
                     tma_load_2d(sbase + pl.off_x + s * pl.stage_bytes + (uint32_t)b * 16384u,
                                 &tmX, bar_full + 8u * s, b * 32, row0, kEvictFirst);
+                if (ptile >= 0)
+                    for (int b = 0; b < pl.nblkX; ++b)
+                        tma_prefetch_2d(&tmX, b * 32, (int32_t)(ptile * kTile));
             }
             __syncwarp();
             PIXIE_TRACE(0, seq0 + it);
@@ -851,11 +868,16 @@ bmu_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ T
         // ============================================================ TMA producer, train mode
         // Runs through ALL steps on its own: X does not depend on the codebook, so the next step's
         // first tiles are already in flight while the other warps finish the current step.
+        StepTiles stp = step_tiles(p, 0);
+        uint32_t cnt = tiles_of(stp);
         for (int st = 0; st < nsteps; ++st) {
-            const StepTiles stp = step_tiles(p, st);
-            const uint32_t cnt = tiles_of(stp);
-            produce_step(stp, cnt, base_seq, st);
+            const bool more = st + 1 < nsteps;
+            const StepTiles nxt = more ? step_tiles(p, st + 1) : StepTiles{0, 0, 0};
+            const uint32_t nxt_cnt = more ? tiles_of(nxt) : 0u;
+            produce_step(stp, cnt, base_seq, st, nxt, nxt_cnt);
             base_seq += cnt;
+            stp = nxt;
+            cnt = nxt_cnt;
         }
     } else {
     for (int st = 0; st < nsteps; ++st) {
@@ -865,7 +887,7 @@ bmu_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ T
     if (warp == NEPI) {
         // ============================================================ TMA producer (assignment)
         load_image();
-        produce_step(stp, cnt, base_seq, st);
+        produce_step(stp, cnt, base_seq, st, StepTiles{0, 0, 0}, 0u);
     } else if (warp == NEPI + 1) {
         // ============================================================ MMA issuer
         // The whole warp walks the loop and waits on the barriers; one elected lane (always the

@@ -125,7 +125,7 @@ struct TcParams {
     int dbg_step0;         // PIXIE_PROFILE builds: first of the two steps whose events are traced
     unsigned long long *trace;  // ... into this buffer (null in production builds)
     unsigned int *trace_count;
-    int dbg_flags;         // experiments (PIXIE_DBG_FLAGS); 4 = per-step printf in PIXIE_PROFILE builds
+    int dbg_flags;         // experiments (PIXIE_DBG_FLAGS); 4 = per-step printf in PIXIE_PROFILE builds, 8 = no L2 prefetch
     float delta_scale;     // 1 in production; tests shrink the candidate window to probe its margin
     TcPlan plan;
 };

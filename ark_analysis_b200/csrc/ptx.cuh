@@ -104,6 +104,16 @@ __device__ __forceinline__ void tma_load_2d(uint32_t dst_smem, const void *tmap,
           "l"(cache_hint)
         : "memory");
 }
+// Same box, but only as far as L2: no shared memory, no barrier.  The producer issues it one stage
+// cycle ahead of the real load, which then finds its lines in L2 (shorter and steadier latency
+// than HBM under load: profiles/r02_notes.md section 8).
+__device__ __forceinline__ void tma_prefetch_2d(const void *tmap, int32_t c0, int32_t c1)
+{
+    asm volatile("cp.async.bulk.prefetch.tensor.2d.L2.global.tile [%0, {%1, %2}];"
+                 :
+                 : "l"(reinterpret_cast<uint64_t>(tmap)), "r"(c0), "r"(c1)
+                 : "memory");
+}
 // 1-D bulk copy global -> shared, completion on an mbarrier.  bytes % 16 == 0.
 __device__ __forceinline__ void bulk_load(uint32_t dst_smem, const void *src, uint32_t bytes,
                                           uint32_t bar)
