@@ -173,13 +173,71 @@ TcPlan make_tc_plan(int C, int K, bool acc)
     return best;
 }
 
+// Split-operand assignment kernel (bmu_x3_kernel.cuh).  Shared memory, from the 1 KiB-aligned base:
+// image = [hi block | lo block | bias block] (rows rounded up to 8, not to the MMA's N: the
+// columns of the rows it reads past the block are never looked at), the barriers in the gap up to
+// the next KiB, the ones tile, eight X stages, four low-part buffers.  At K = 100, C = 32 that is
+// 231,424 bytes, all a CTA can have: hence the shape limits.
+TcPlan make_x3_plan(int C, int K)
+{
+    TcPlan p{};
+    p.ok = false;
+    if (C < 1 || C > 32 || K < 1 || K > 104) return p;
+    const int mode = env_int("PIXIE_X3", 1);  // 0 = never, 1 = where it is faster, 2 = wherever it fits
+    if (mode == 0) return p;
+    if (mode == 1 && C > 24) return p;  // four K-steps x 3 MMAs: tensor-pipe bound, slower than plain
+    static const int kSl[][2] = {{32, 1}, {32, 2}, {48, 2}, {50, 2}, {52, 2}};
+    int pick = -1;
+    for (int i = 0; i < 5; ++i)
+        if (kSl[i][0] * kSl[i][1] >= K) {
+            pick = i;
+            break;
+        }
+    if (pick < 0) return p;
+    p.C = C;
+    p.K = K;
+    p.C8 = (C + 7) / 8 * 8;
+    p.ksteps = p.C8 / 8;
+    p.nblkX = 1;
+    p.nblkW = 1;
+    p.SL = kSl[pick][0];
+    p.spc = kSl[pick][1];
+    p.NCH = 1;
+    p.NG = 4;
+    p.Nchunk = p.SL * p.spc;
+    p.Nmma = (p.Nchunk + 15) / 16 * 16;
+    p.Ntot = (p.Nchunk + 7) / 8 * 8;  // image rows per block
+    p.nbuf = 4;
+    p.tmem_cols = 32;
+    while (p.tmem_cols < 4 * p.Nmma) p.tmem_cols *= 2;
+    p.stage_bytes = 16384u;
+    p.x3 = 1;
+    p.off_wlo = (uint32_t)p.Ntot * 128u;
+    p.off_bias = 2u * p.off_wlo;
+    p.wimg_bytes = p.off_bias + (uint32_t)p.Ntot * 32u;
+    p.off_bar = (p.wimg_bytes + 15u) / 16u * 16u;
+    p.off_ones = (p.off_bar + (uint32_t)kBarBlock + 1023u) / 1024u * 1024u;
+    p.off_x = p.off_ones + 4096u;
+    p.nstage = 8;
+    p.off_xl = p.off_x + 8u * p.stage_bytes;
+    p.smem_need = p.off_xl + 4u * p.stage_bytes;
+    // 227 KiB per CTA minus the KiB the toolchain reserves (cuobjdump: SHARED:1024).  K = 100 needs
+    // exactly this much: no alignment slack is left, the kernel traps if the base is not aligned.
+    const uint32_t limit = 226u * 1024u;
+    if (p.smem_need > limit) return p;
+    p.smem_bytes = p.smem_need + 1024u > limit ? limit : p.smem_need + 1024u;
+    p.ok = true;
+    return p;
+}
+
 // ------------------------------------------------------------------------------------------------
 // codebook preparation: W [K x C] fp32  ->  shared-memory image + norms
 // ------------------------------------------------------------------------------------------------
 // one warp per codebook row; lanes stride over the image columns (coalesced reads of W)
 __global__ void __launch_bounds__(256)
 codebook_prep_kernel(const float *__restrict__ W, int K, int C, int nblkW, int Ntot,
-                     uint32_t off_bias, float *__restrict__ wimg, CodebookAux *__restrict__ aux)
+                     uint32_t off_bias, uint32_t off_wlo, float *__restrict__ wimg,
+                     CodebookAux *__restrict__ aux)
 {
     const int lane = threadIdx.x & 31;
     const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
@@ -198,6 +256,10 @@ codebook_prep_kernel(const float *__restrict__ W, int K, int C, int nblkW, int N
             v = -2.0f * w;
         }
         *reinterpret_cast<float *>(base + img_offset(Ntot, row, col)) = v;
+        // split-operand kernel: what the tensor core drops from v (it reads the top 19 bits)
+        if (off_wlo)
+            *reinterpret_cast<float *>(base + off_wlo + img_offset(Ntot, row, col)) =
+                v - __uint_as_float(__float_as_uint(v) & 0xFFFFE000u);
     }
     for (int o = 16; o > 0; o >>= 1) nrm2 += __shfl_xor_sync(~0u, nrm2, o);
     bad = __any_sync(~0u, bad);
@@ -233,7 +295,7 @@ cudaError_t launch_codebook_prep(const float *W, int K, int C, const TcPlan &pla
 {
     const int rows_per_block = 8;
     codebook_prep_kernel<<<(plan.Ntot + rows_per_block - 1) / rows_per_block, 256, 0, stream>>>(
-        W, K, C, plan.nblkW, plan.Ntot, plan.off_bias, wimg, aux);
+        W, K, C, plan.nblkW, plan.Ntot, plan.off_bias, plan.x3 ? plan.off_wlo : 0u, wimg, aux);
     count_launch();
     return cudaGetLastError();
 }

@@ -171,6 +171,11 @@ int bmu_tiles(const float *X, int64_t n, int C, int64_t ldX, const float *W, int
     TcPlan plan = make_tc_plan(C, K, SN != nullptr);
     bool fused = SN != nullptr && plan.ok;
     if (!plan.ok && SN != nullptr) plan = make_tc_plan(C, K, false);
+    if (!fused) {
+        // the default Pixie shape has a faster kernel of its own (split tf32 operands)
+        const TcPlan x3 = make_x3_plan(C, K);
+        if (x3.ok) plan = x3;
+    }
     const bool aligned = ((reinterpret_cast<uintptr_t>(X) & 15u) == 0) && (ldX % 4 == 0) &&
                          ldX >= C && n < ((int64_t)1 << 31) - kTile;
     bool use_tc = plan.ok && aligned && !(flags & PIXIE_FLAG_FORCE_EXACT);
@@ -206,7 +211,10 @@ int bmu_tiles(const float *X, int64_t n, int C, int64_t ldX, const float *W, int
         p.dbg_flags = getenv("PIXIE_DBG_FLAGS") ? atoi(getenv("PIXIE_DBG_FLAGS")) : 0;
         p.plan = plan;
         if (fused) PX_CUDA(clear_group_tables(plan, ws, stream));
-        PX_CUDA(launch_bmu_tc(tm, p, sum_parts(), stream));
+        if (plan.x3)
+            PX_CUDA(launch_bmu_x3(tm, p, sum_parts(), stream));
+        else
+            PX_CUDA(launch_bmu_tc(tm, p, sum_parts(), stream));
         // rows the tensor-core kernel could not settle (NaN/Inf rows, degenerate codebooks): exact
         // kernel; returns immediately when the counter is zero.  In fused mode it also adds those
         // rows to SN.

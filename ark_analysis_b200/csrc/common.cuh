@@ -70,6 +70,12 @@ struct TcPlan {
     int pair_cap;               // pair-list capacity per epilogue warp
     uint32_t pairs_bytes;       // bytes at off_pairs (pair lists; scratch of the end-of-step work)
     uint32_t smem_bytes;  // dynamic shared memory to request (includes 1 KiB alignment slack)
+    // split-operand assignment kernel (bmu_x3_kernel.cuh; make_x3_plan): the image holds a second
+    // set of blocks with the low parts of -2 W at off_wlo, and every epilogue group owns a buffer
+    // for the low parts of its next X tile at off_xl + g * stage_bytes
+    int x3;
+    uint32_t off_wlo, off_xl;
+    uint32_t smem_need;   // bytes used from the 1 KiB-aligned base (smem_bytes - alignment slack)
 };
 
 // Train-mode statistics.  Global tables (group tables that do not fit on chip, CTA parts):
@@ -84,6 +90,10 @@ __host__ __device__ inline int tab_pitch(int C) { return (C + 3) & ~3; }
 // caps the pipeline depth, PIXIE_TAB_GLOBAL=1/0 forces / forbids global tables (environment,
 // experiments only).
 TcPlan make_tc_plan(int C, int K, bool acc = false);
+// Plan of the split-operand ("3 x tf32") assignment kernel: K <= 104 and C <= 24 (C <= 32 fits in
+// shared memory -- beside eight X stages and four low-part buffers -- but is slower than the plain
+// kernel; PIXIE_X3=2 takes it anyway, PIXIE_X3=0 never: A/B runs and tests).
+TcPlan make_x3_plan(int C, int K);
 
 struct TcParams {
     int64_t n;             // rows of X
@@ -134,6 +144,8 @@ struct TcParams {
 cudaError_t launch_codebook_prep(const float *W, int K, int C, const TcPlan &plan, float *wimg,
                                  CodebookAux *aux, cudaStream_t stream);
 cudaError_t launch_bmu_tc(const CUtensorMap &tmX, const TcParams &p, int num_sms,
+                          cudaStream_t stream);
+cudaError_t launch_bmu_x3(const CUtensorMap &tmX, const TcParams &p, int num_sms,
                           cudaStream_t stream);
 cudaError_t launch_bmu_exact(const float *X, int64_t n, int C, int64_t ldX, const float *W, int K,
                              int32_t *labels, int64_t tile_first, int64_t tile_stride,

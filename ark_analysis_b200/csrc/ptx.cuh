@@ -288,6 +288,14 @@ __device__ __forceinline__ uint4 lds128(uint32_t addr)
     return r;
 }
 
+// 128-bit shared-memory store to a 32-bit shared address
+__device__ __forceinline__ void sts128(uint32_t addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d)
+{
+    asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(a), "r"(b), "r"(c),
+                 "r"(d)
+                 : "memory");
+}
+
 // ---------------------------------------------------------------- packed fp32 (FADD2 / FFMA2)
 __device__ __forceinline__ uint64_t pack2(float lo, float hi)
 {

@@ -314,6 +314,66 @@ def test_candidate_window_has_margin(monkeypatch):
     assert flagged[1] < 0.6 * flagged[0]
 
 
+@pytest.mark.parametrize("C,K", [(16, 100), (24, 64), (32, 100), (7, 33), (20, 104), (32, 96)])
+def test_split_operand_kernel_hard_cases(monkeypatch, C, K):
+    """The split-operand (3 x tf32) assign kernel (csrc/bmu_x3_kernel.cuh; taken for C <= 24,
+    K <= 104, forced here up to C = 32) against the exact fp64 kernel on the inputs that stress a
+    narrow candidate window: codebooks of near-identical node pairs (every row has two candidates a
+    few ulp apart), rows equal to nodes, mixed signs, values x 1000, NaN / Inf rows, a ragged tail."""
+    monkeypatch.setenv("PIXIE_X3", "2")
+    n = 128 * 700 + 37
+    X = pixie_like(n, C, seed=31 + C)
+    W = X[np.random.default_rng(K).choice(n, K, replace=False)].copy()
+    W[1::2] = W[:-1:2][: len(W[1::2])] * (1 + 2.0 ** -19)
+    X[::53] = W[np.arange(len(X[::53])) % K]
+    cases = {"pairs": (X, W), "x1000": (X * 1000, W * 1000), "signed": (X - 0.03, W - 0.03)}
+    Xn = X.copy()
+    Xn[11::401, C // 2] = np.nan
+    Xn[12::401, 0] = np.inf
+    cases["nan rows"] = (Xn, W)
+    for name, (x, w) in cases.items():
+        x = np.ascontiguousarray(x, dtype=np.float32)
+        w = np.ascontiguousarray(w, dtype=np.float32)
+        Xd, Wd = S.to_device_matrix(x), torch.from_numpy(w).cuda()
+        want = S.bmu(Xd, Wd, flags=S.FLAG_FORCE_EXACT)
+        stats = torch.zeros(S.NSTATS, dtype=torch.int64, device="cuda")
+        got = S.bmu(Xd, Wd, flags=S.FLAG_FORCE_TC, stats=stats)
+        torch.cuda.synchronize()
+        assert torch.equal(got, want), name
+        assert int(stats[4]) == 1
+    # and against the oracle itself on a slice (the exact kernel is checked against it elsewhere)
+    ref, _ = oracle.map_data_to_nodes_f32(W, X[:20000])
+    np.testing.assert_array_equal(S.bmu(S.to_device_matrix(X[:20000]),
+                                        torch.from_numpy(W).cuda()).cpu().numpy(), ref)
+
+
+def test_split_operand_window_has_margin(monkeypatch):
+    """The accumulation part of the split-operand kernel's window rests on a model of the tensor
+    core's fp32 accumulator plus measurement (bmu_x3_kernel.cuh, scripts/x3_margin.py): labels must
+    stay identical to the exact kernel with the window shrunk 16-fold, on plain rows and on a
+    codebook of near-identical node pairs, and the plain kernel's recheck load must be gone."""
+    X = S.to_device_matrix(pixie_like(1 << 21, 16, seed=8))
+    W = X[:100].contiguous()
+    W2 = W.clone()
+    W2[1::2] = W2[::2] * (1 + 2.0 ** -18)
+    for Wd in (W, W2):
+        ref = S.bmu(X, Wd, flags=S.FLAG_FORCE_EXACT)
+        for scale in ("1", "0.0625"):
+            monkeypatch.setenv("PIXIE_DELTA_SCALE", scale)
+            stats = torch.zeros(S.NSTATS, dtype=torch.int64, device="cuda")
+            lab = S.bmu(X, Wd, flags=S.FLAG_FORCE_TC, stats=stats)
+            torch.cuda.synchronize()
+            assert torch.equal(lab, ref), scale
+            if Wd is W and scale == "1":
+                split_flagged = int(stats[0])
+        monkeypatch.delenv("PIXIE_DELTA_SCALE")
+    monkeypatch.setenv("PIXIE_X3", "0")
+    stats = torch.zeros(S.NSTATS, dtype=torch.int64, device="cuda")
+    S.bmu(X, W, flags=S.FLAG_FORCE_TC, stats=stats)
+    torch.cuda.synchronize()
+    assert split_flagged < 0.05 * int(stats[0])
+
+
 def test_concurrent_host_threads_share_nothing():
     """cluster_pixels(multiprocess=True) labels FOVs from a thread pool; ctypes releases the GIL, so
     the memset -> prep -> BMU -> fix-up chains of several threads interleave on one stream.  Each
