@@ -44,17 +44,33 @@ __device__ __forceinline__ void som_update_nodes(const double *SN, double *W64, 
     for (int k0 = kfirst; k0 < K; k0 += kstride * kUpdNodes) {
         int nk = 0;
         while (nk < kUpdNodes && k0 + nk * kstride < K) ++nk;
-        // ---- neighbourhood weights of this sweep's nodes
-        for (int i = tid; i < nk * K; i += nthr) {
-            const int j = i / K, b = i - j * K;
-            const int k = k0 + j * kstride;
-            const int dx = abs(k / ydim - b / ydim), dy = abs(k % ydim - b % ydim);
-            const double d = (double)(dx > dy ? dx : dy);
-            const double cnt = __ldcg(SN + (size_t)b * ld + C);
-            s_h[j * K + b] = cnt == 0.0 ? 0.0 : exp(-d * d * inv2s2);  // empty nodes are skipped
+        // ---- neighbourhood weights of this sweep's nodes.  The node counts come from L2 (~1 us a
+        // round trip): a thread fetches those of all its (node, b) pairs before the first exp().
+        for (int i0 = tid; i0 < nk * K; i0 += 4 * nthr) {
+            double cnt[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const int i = i0 + u * nthr;
+                cnt[u] = i < nk * K ? __ldcg(SN + (size_t)(i % K) * ld + C) : 0.0;
+            }
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const int i = i0 + u * nthr;
+                if (i < nk * K) {
+                    const int j = i / K, b = i - j * K;
+                    const int k = k0 + j * kstride;
+                    const int dx = abs(k / ydim - b / ydim), dy = abs(k % ydim - b % ydim);
+                    const double d = (double)(dx > dy ? dx : dy);
+                    s_h[j * K + b] = cnt[u] == 0.0 ? 0.0 : exp(-d * d * inv2s2);  // empty nodes are skipped
+                }
+            }
         }
         sync();
-        // ---- sliced dot products: warp task = (slice s, 32-column block cb), lanes = columns
+        // ---- sliced dot products: warp task = (slice s, 32-column block cb), lanes = columns.
+        // Sixteen rows of SN are in flight per lane (this phase is nothing but L2 latency: with
+        // four, a 20 x 20 map took 13 round trips per task, 31 us per step); the adds stay in
+        // ascending b order.
+        constexpr int kInFlight = 16;
         for (int task = warp; task < kUpdSlices * ncb; task += nwarps) {
             const int s = task % kUpdSlices, cb = task / kUpdSlices;
             const int c = cb * 32 + lane;
@@ -63,22 +79,22 @@ __device__ __forceinline__ void som_update_nodes(const double *SN, double *W64, 
             for (int j = 0; j < kUpdNodes; ++j) acc[j] = 0.0;
             if (c < ld) {
                 const double *col = SN + c;
-                int b = s;
-                for (; b + 3 * kUpdSlices < K; b += 4 * kUpdSlices) {
-                    double v[4];
+                for (int b0 = s; b0 < K; b0 += kInFlight * kUpdSlices) {
+                    double v[kInFlight];
 #pragma unroll
-                    for (int u = 0; u < 4; ++u) v[u] = __ldcg(col + (size_t)(b + u * kUpdSlices) * ld);
+                    for (int u = 0; u < kInFlight; ++u) {
+                        const int b = b0 + u * kUpdSlices;
+                        v[u] = b < K ? __ldcg(col + (size_t)b * ld) : 0.0;
+                    }
 #pragma unroll
-                    for (int u = 0; u < 4; ++u)
+                    for (int u = 0; u < kInFlight; ++u) {
+                        const int b = b0 + u * kUpdSlices;
+                        if (b < K) {
 #pragma unroll
-                        for (int j = 0; j < kUpdNodes; ++j)
-                            if (j < nk) acc[j] = fma(s_h[j * K + b + u * kUpdSlices], v[u], acc[j]);
-                }
-                for (; b < K; b += kUpdSlices) {
-                    const double v = __ldcg(col + (size_t)b * ld);
-#pragma unroll
-                    for (int j = 0; j < kUpdNodes; ++j)
-                        if (j < nk) acc[j] = fma(s_h[j * K + b], v, acc[j]);
+                            for (int j = 0; j < kUpdNodes; ++j)
+                                if (j < nk) acc[j] = fma(s_h[j * K + b], v[u], acc[j]);
+                        }
+                    }
                 }
 #pragma unroll
                 for (int j = 0; j < kUpdNodes; ++j)

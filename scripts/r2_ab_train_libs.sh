@@ -1,0 +1,5 @@
+for rep in 1 2 3; do
+for shape in "5241600 32 10 10" "3355392 40 20 20"; do
+  echo "head: $(PIXIE_LIB_PATH=$PWD/ark_analysis_b200/_lib/libpixie_b200_head.so python scripts/prof_train_pass.py $shape 5 2>&1 | tail -2 | tr '\n' ' ')"
+  echo "new : $(PIXIE_LIB_PATH=$PWD/ark_analysis_b200/_lib/libpixie_b200_new.so python scripts/prof_train_pass.py $shape 5 2>&1 | tail -2 | tr '\n' ' ')"
+done; done
