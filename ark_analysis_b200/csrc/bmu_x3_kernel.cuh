@@ -68,14 +68,17 @@ bmu_x3_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ T
     constexpr uint32_t NST = kX3Stages;
     static_assert(NG * NMMA <= 512, "four accumulator buffers must fit in TMEM");
 
-    extern __shared__ uint8_t smem_raw[];
+    // K = 97..104 needs every byte a CTA can have, so the 1 KiB alignment the swizzled tiles need
+    // is asked of the declaration instead of being padded for; should a toolchain not honour it,
+    // the launch fails (trap) rather than run past the allocation.
+    extern __shared__ __align__(1024) uint8_t smem_x3[];
     const TcPlan &pl = p.plan;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
-    const uint32_t raw_u32 = smem_u32(smem_raw);
+    const uint32_t raw_u32 = smem_u32(smem_x3);
     const uint32_t pad = (1024u - (raw_u32 & 1023u)) & 1023u;
-    if (pad + pl.smem_need > pl.smem_bytes) __trap();  // the carve-up below would not fit
-    uint8_t *smem = smem_raw + pad;
+    if (pad + pl.smem_need > pl.smem_bytes) __trap();
+    uint8_t *smem = smem_x3 + pad;
     const uint32_t sbase = raw_u32 + pad;
     uint8_t *ws = smem;  // codebook image: hi block (full-precision -2 W), lo block, bias block
     uint8_t *ones = smem + pl.off_ones;
