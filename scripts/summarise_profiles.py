@@ -22,15 +22,17 @@ for r in csv.DictReader(io.StringIO("".join(lines))):
         rows.append((int(r["ID"]), r["Kernel Name"], v))
 open(f"profiles/{tag}_bench_launches.csv", "w").write("".join(lines))
 # one steady-state bench step = [som_apply, codebook_prep, whole-pass kernel (ACC variant, "..., 1>"),
-# codebook_prep, assign kernel ("..., 0>"), bmu_exact fix-up]; take the last complete one before the
-# verification / end-to-end legs (whose launches follow in the list)
-acc = [i for i, (_, k, _) in enumerate(rows) if "bmu_tc_kernel" in k and ", 1>" in k]
-i = acc[-2]  # the last ACC launch belongs to the end-to-end leg (chunked assign behind it)
-step = rows[i - 2:i + 4]
+# codebook_prep, assign kernel ("..., 0>"), bmu_exact fix-up]; take the last such window of full-size
+# launches (the oracle check on a sampled shard and the chunked end-to-end leg follow in the list)
+pat = ["som_apply", "codebook_prep", ", 1>", "codebook_prep", ", 0>", "bmu_exact"]
+wins = [i for i in range(len(rows) - 5)
+        if all(pat[j] in rows[i + j][1] for j in range(6)) and rows[i + 2][2] > 1.0 and rows[i + 4][2] > 1.0]
+i = wins[-1]
+step = rows[i:i + 6]
 tot = sum(v for _, _, v in step)
 with open(f"profiles/{tag}_bench_launches_summary.txt", "w") as f:
     f.write("ncu --metrics gpu__time_duration.sum --clock-control none --kernel-name-base mangled "
-            "-k regex:5pixie -c 80: python bench.py --steps 2 --warmup 3 (N=1)\n"
+            "-k regex:5pixie -c 80: python bench.py --steps 2 --warmup 3 --no-cfg3 (N=1)\n"
             "Only this library's kernels are listed (the synthetic-data generation is torch and is "
             "filtered out).  The list holds 5 bench steps (3 warm-up + 2 timed), the bench's exact-kernel "
             "spot check (one 3.1 ms bmu_exact launch) and the chunked launches of the end-to-end leg.\n"
