@@ -96,8 +96,16 @@ TcPlan make_tc_plan(int C, int K, bool acc)
         if (need > 512) continue;
         p.tmem_cols = 32;
         while (p.tmem_cols < need) p.tmem_cols *= 2;
+        p.tail8 = (p.C8 % 32 == 8 && p.nblkX >= 2 && p.nblkX == p.nblkW &&
+                   env_int("PIXIE_TAIL8", 1) != 0) ? 1 : 0;
         p.stage_bytes = (uint32_t)p.nblkX * 16384u;
         p.off_bias = (uint32_t)p.nblkW * (uint32_t)p.Ntot * 128u;
+        if (p.tail8) {
+            p.x_tail_off = (uint32_t)(p.nblkX - 1) * 16384u;
+            p.stage_bytes = p.x_tail_off + 4096u;
+            p.w_tail_off = (uint32_t)(p.nblkW - 1) * (uint32_t)p.Ntot * 128u;
+            p.off_bias = (p.w_tail_off + (uint32_t)p.Ntot * 32u + 1023u) / 1024u * 1024u;
+        }
         p.wimg_bytes = p.off_bias + (uint32_t)p.Ntot * 32u;
         p.off_ones = (p.wimg_bytes + 1023u) / 1024u * 1024u;
         p.off_x = p.off_ones + 4096u;
@@ -235,14 +243,16 @@ TcPlan make_x3_plan(int C, int K)
 // ------------------------------------------------------------------------------------------------
 // one warp per codebook row; lanes stride over the image columns (coalesced reads of W)
 __global__ void __launch_bounds__(256)
-codebook_prep_kernel(const float *__restrict__ W, int K, int C, int nblkW, int Ntot,
+codebook_prep_kernel(const float *__restrict__ W, int K, int C, int nblkW, int lay,
                      uint32_t off_bias, uint32_t off_wlo, float *__restrict__ wimg,
                      CodebookAux *__restrict__ aux)
 {
+    const int Ntot = lay & 0xFFFF;  // rows per block; the high half marks a tail8 last block
     const int lane = threadIdx.x & 31;
     const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     if (row >= Ntot) return;
-    const int ncols = nblkW * 32;
+    const int tb = (lay >> 16) - 1;
+    const int ncols = tb >= 0 ? tb * 32 + 8 : nblkW * 32;  // a tail8 block is 8 columns wide
     char *base = reinterpret_cast<char *>(wimg);
     double nrm2 = 0.0;
     bool bad = false, neg = false;
@@ -255,10 +265,10 @@ codebook_prep_kernel(const float *__restrict__ W, int K, int C, int nblkW, int N
             nrm2 += (double)w * (double)w;
             v = -2.0f * w;
         }
-        *reinterpret_cast<float *>(base + img_offset(Ntot, row, col)) = v;
+        *reinterpret_cast<float *>(base + img_offset(lay, row, col)) = v;
         // split-operand kernel: what the tensor core drops from v (it reads the top 19 bits)
         if (off_wlo)
-            *reinterpret_cast<float *>(base + off_wlo + img_offset(Ntot, row, col)) =
+            *reinterpret_cast<float *>(base + off_wlo + img_offset(lay, row, col)) =
                 v - __uint_as_float(__float_as_uint(v) & 0xFFFFE000u);
     }
     for (int o = 16; o > 0; o >>= 1) nrm2 += __shfl_xor_sync(~0u, nrm2, o);
@@ -295,7 +305,8 @@ cudaError_t launch_codebook_prep(const float *W, int K, int C, const TcPlan &pla
 {
     const int rows_per_block = 8;
     codebook_prep_kernel<<<(plan.Ntot + rows_per_block - 1) / rows_per_block, 256, 0, stream>>>(
-        W, K, C, plan.nblkW, plan.Ntot, plan.off_bias, plan.x3 ? plan.off_wlo : 0u, wimg, aux);
+        W, K, C, plan.nblkW, lay_pack(plan.Ntot, plan.tail8 ? plan.nblkW - 1 : -1), plan.off_bias,
+        plan.x3 ? plan.off_wlo : 0u, wimg, aux);
     count_launch();
     return cudaGetLastError();
 }

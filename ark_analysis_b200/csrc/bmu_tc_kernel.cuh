@@ -67,9 +67,19 @@ constexpr unsigned int kTraceCap = 1u << 15;
 // core-matrix layout (bias_offset), columns 0..2 = ||w_k||^2 split into three tf32-exact terms
 // (multiplied by the all-ones A tile of the bias K-step); rows >= K hold zeros and a huge bias so
 // they never win.
-__device__ __forceinline__ uint32_t img_offset(int Ntot, int row, int col)
+// `lay` = rows per image block (Ntot, < 65536) in the low half and, when the last block is a
+// "tail8" block (TcPlan::tail8: 32-byte rows, SWIZZLE_32B), its index + 1 in the high half.
+__host__ __device__ __forceinline__ int lay_pack(int Ntot, int tail_blk_or_neg)
 {
+    return Ntot | ((tail_blk_or_neg + 1) << 16);
+}
+__device__ __forceinline__ uint32_t img_offset(int lay, int row, int col)
+{
+    const int Ntot = lay & 0xFFFF, tb = (lay >> 16) - 1;
     const int b = col >> 5, cc = col & 31;
+    if (b == tb)
+        return (uint32_t)b * (uint32_t)Ntot * 128u + (uint32_t)row * 32u +
+               (uint32_t)((((cc >> 2) ^ ((row >> 2) & 1)) << 4) + ((cc & 3) << 2));
     return (uint32_t)b * (uint32_t)Ntot * 128u + (uint32_t)row * 128u +
            (uint32_t)((((cc >> 2) ^ (row & 7)) << 4) + ((cc & 3) << 2));
 }
@@ -87,14 +97,23 @@ __host__ __device__ __forceinline__ uint32_t bias_offset(int row, int col)
 // ------------------------------------------------------------------------------------------------
 // Both the X stages (written by TMA SWIZZLE_128B) and the codebook image keep logical 16-byte
 // chunk c of row r of a 32-column block at physical chunk (c ^ (r & 7)).
-__device__ __forceinline__ const float4 *x_chunk_ptr(const uint8_t *xs, int row, int blk, int chunk)
+__device__ __forceinline__ const float4 *x_chunk_ptr(const uint8_t *xs, int lay, int row, int blk,
+                                                     int chunk)
 {
+    if (blk == (lay >> 16) - 1)
+        return reinterpret_cast<const float4 *>(xs + (size_t)blk * 16384u + (size_t)row * 32u +
+                                                (size_t)(((chunk ^ (row >> 2)) & 1) << 4));
     return reinterpret_cast<const float4 *>(xs + (size_t)blk * 16384u + (size_t)row * 128u +
                                             (size_t)(((chunk ^ (row & 7)) & 7) << 4));
 }
-__device__ __forceinline__ const float4 *w_chunk_ptr(const uint8_t *ws, int Ntot, int node, int blk,
+__device__ __forceinline__ const float4 *w_chunk_ptr(const uint8_t *ws, int lay, int node, int blk,
                                                      int chunk)
 {
+    const int Ntot = lay & 0xFFFF;
+    if (blk == (lay >> 16) - 1)
+        return reinterpret_cast<const float4 *>(ws + (size_t)blk * (size_t)Ntot * 128u +
+                                                (size_t)node * 32u +
+                                                (size_t)(((chunk ^ (node >> 2)) & 1) << 4));
     return reinterpret_cast<const float4 *>(ws + (size_t)blk * (size_t)Ntot * 128u +
                                             (size_t)node * 128u +
                                             (size_t)(((chunk ^ (node & 7)) & 7) << 4));
@@ -118,9 +137,10 @@ __device__ __forceinline__ void dist2_chunk(const float4 x, const float4 w, uint
 // DIFFERENT rows, and chunk pc of eight different rows is one 16-byte bank group -- an 8-way
 // conflict -- while chunks pc ^ rot spread a quarter-warp over all eight groups.
 // The last, partial block is walked logically so the bias columns of the image are never read.
-__device__ __forceinline__ float pair_dist2_f32(const uint8_t *xs, const uint8_t *ws, int Ntot,
+__device__ __forceinline__ float pair_dist2_f32(const uint8_t *xs, const uint8_t *ws, int lay,
                                                 int nchunks16, int row, int node, uint32_t rot)
 {
+    const int Ntot = lay & 0xFFFF;
     const uint64_t half2 = pack2(0.5f, 0.5f);
     uint64_t acc0 = 0ull, acc1 = 0ull;
     const int nfull = nchunks16 >> 3;
@@ -144,8 +164,8 @@ __device__ __forceinline__ float pair_dist2_f32(const uint8_t *xs, const uint8_t
     }
     const int rem = nchunks16 & 7;
     for (int lc = 0; lc < rem; ++lc) {
-        const float4 x = *x_chunk_ptr(xs, row, nfull, lc);
-        const float4 w = *w_chunk_ptr(ws, Ntot, node, nfull, lc);
+        const float4 x = *x_chunk_ptr(xs, lay, row, nfull, lc);
+        const float4 w = *w_chunk_ptr(ws, lay, node, nfull, lc);
         dist2_chunk(x, w, half2, acc0, acc1);
     }
     float a, b, c, d;
@@ -158,10 +178,12 @@ __device__ __forceinline__ float pair_dist2_f32(const uint8_t *xs, const uint8_t
 // one walk over the row (the common case: a flagged row has exactly two candidates).  The thread
 // reads ITS OWN row, chunk c at physical chunk c ^ (row & 7), so a quarter-warp (8 consecutive
 // rows) covers all eight bank groups; codebook chunks follow the same logical order.
-__device__ __forceinline__ void duel_dist2_f32(const uint8_t *xs, const uint8_t *ws, int Ntot,
+__device__ __forceinline__ void duel_dist2_f32(const uint8_t *xs, const uint8_t *ws, int lay,
                                                int nchunks16, int row, int na, int nb, float &da,
                                                float &db)
 {
+    const int Ntot = lay & 0xFFFF;
+    const bool tail = (lay >> 16) != 0;
     const uint64_t half2 = pack2(0.5f, 0.5f);
     uint64_t a0 = 0ull, a1 = 0ull, b0 = 0ull, b1 = 0ull;
     // rows are 128-byte aligned: OR the row's swizzle key in, XOR the logical chunk index
@@ -185,10 +207,17 @@ __device__ __forceinline__ void duel_dist2_f32(const uint8_t *xs, const uint8_t 
                             half2, b0, b1);
             }
         } else {
+            // partial last block; a tail8 block keeps 32-byte rows (chunk c at c ^ ((r >> 2) & 1))
+            uint32_t xr = xrow, ra = wa, rb = wb;
+            if (tail) {
+                xr = (xrow & ~0x7Fu) - (uint32_t)row * 96u + ((((uint32_t)row >> 2) & 1u) << 4);
+                ra = (wa & ~0x7Fu) - (uint32_t)na * 96u + ((((uint32_t)na >> 2) & 1u) << 4);
+                rb = (wb & ~0x7Fu) - (uint32_t)nb * 96u + ((((uint32_t)nb >> 2) & 1u) << 4);
+            }
             for (uint32_t c = 0; c < (uint32_t)left; ++c) {
-                const uint4 xu = lds128(xrow ^ (c << 4));
-                const uint4 au = lds128(wa ^ (c << 4));
-                const uint4 bu = lds128(wb ^ (c << 4));
+                const uint4 xu = lds128(xr ^ (c << 4));
+                const uint4 au = lds128(ra ^ (c << 4));
+                const uint4 bu = lds128(rb ^ (c << 4));
                 const float4 x = make_float4(__uint_as_float(xu.x), __uint_as_float(xu.y),
                                              __uint_as_float(xu.z), __uint_as_float(xu.w));
                 dist2_chunk(x, make_float4(__uint_as_float(au.x), __uint_as_float(au.y),
@@ -215,14 +244,14 @@ __device__ __forceinline__ void duel_dist2_f32(const uint8_t *xs, const uint8_t 
 // stage 3: the reference's fp64 operation sequence for one (row, node) pair
 // (oracle/pixie_oracle.c nearest_node): tmp = x - w; acc = acc + tmp * tmp (separately rounded),
 // in channel order; d = sqrt(acc).
-static __device__ __noinline__ double pair_dist_f64(const uint8_t *xs, const uint8_t *ws, int Ntot, int C,
+static __device__ __noinline__ double pair_dist_f64(const uint8_t *xs, const uint8_t *ws, int lay, int C,
                                              int row, int node)
 {
     double acc = 0.0;
     for (int j = 0; j < C; ++j) {
         const int blk = j >> 5, cc = j & 31;
-        const float xf = reinterpret_cast<const float *>(x_chunk_ptr(xs, row, blk, cc >> 2))[cc & 3];
-        const float wf = reinterpret_cast<const float *>(w_chunk_ptr(ws, Ntot, node, blk, cc >> 2))[cc & 3];
+        const float xf = reinterpret_cast<const float *>(x_chunk_ptr(xs, lay, row, blk, cc >> 2))[cc & 3];
+        const float wf = reinterpret_cast<const float *>(w_chunk_ptr(ws, lay, node, blk, cc >> 2))[cc & 3];
         const double tmp = __dsub_rn((double)xf, (double)(-0.5f * wf));
         acc = __dadd_rn(acc, __dmul_rn(tmp, tmp));
     }
@@ -370,6 +399,14 @@ __device__ __noinline__ void tile_accumulate_blk(const TcParams &p, uint8_t *sme
         return v;
     };
     const uint32_t my = list_addr + r4 * 8u;
+    // source of chunk ck of a row in block blk; a tail8 block keeps 32-byte rows (row = w0 >> 7,
+    // chunk ck at ck ^ ((row >> 2) & 1); only ck < 2 gets here: last_ok)
+    const bool t8 = pl.tail8 != 0;
+    const uint32_t XT = xs_addr + pl.x_tail_off;
+    auto xsrc = [&](uint32_t xa, uint32_t w0, int blk) -> uint32_t {
+        if (t8 && blk == NBLK - 1) return XT + ((w0 >> 7) << 5) + (((ck ^ (w0 >> 9)) & 1u) << 4);
+        return xa + (uint32_t)blk * 16384u;
+    };
     if constexpr (TABG) {
         // global table: fire and forget, nothing to order
         char *const G = reinterpret_cast<char *>(tab_g) + ck * 16u;
@@ -379,7 +416,7 @@ __device__ __noinline__ void tile_accumulate_blk(const TcParams &p, uint8_t *sme
 #pragma unroll
             for (int blk = 0; blk < NBLK; ++blk) {
                 if (blk < NBLK - 1 || last_ok) {
-                    const float4 x = ldsf4(xa + (uint32_t)blk * 16384u);
+                    const float4 x = ldsf4(xsrc(xa, w0, blk));
                     asm volatile("red.relaxed.gpu.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(
                                      cell + blk * 128),
                                  "f"(x.x), "f"(x.y), "f"(x.z), "f"(x.w)
@@ -404,11 +441,11 @@ __device__ __noinline__ void tile_accumulate_blk(const TcParams &p, uint8_t *sme
         // takes the rows of rank r.  Most batches need one or two rounds.
         const uint32_t T = tab_addr + ck * 16u;
         const uint32_t below = (1u << (r4 * 8u)) - 1u;
-        auto rmw = [&](uint32_t xa, uint32_t ta) {
+        auto rmw = [&](uint32_t xa, uint32_t ta, uint32_t w0) {
             float4 x[NBLK], t[NBLK];
 #pragma unroll
             for (int blk = 0; blk < NBLK; ++blk)
-                if (blk < NBLK - 1 || last_ok) x[blk] = ldsf4(xa + (uint32_t)blk * 16384u);
+                if (blk < NBLK - 1 || last_ok) x[blk] = ldsf4(xsrc(xa, w0, blk));
 #pragma unroll
             for (int blk = 0; blk < NBLK; ++blk)
                 if (blk < NBLK - 1 || last_ok) t[blk] = ldsf4(ta + (uint32_t)blk * 128u);
@@ -428,15 +465,15 @@ __device__ __noinline__ void tile_accumulate_blk(const TcParams &p, uint8_t *sme
             const unsigned same = __match_any_sync(0xffffffffu, w1);
             const int rank = __popc(same & below) >> 3;
             const uint32_t xa = (A ^ (w0 & 0x70u)) + (w0 & 0xFFFFFF80u), ta = T + w1;
-            if (on && rank == 0) rmw(xa, ta);
+            if (on && rank == 0) rmw(xa, ta, w0);
             if (__any_sync(0xffffffffu, rank >= 1)) {
                 __syncwarp();
-                if (on && rank == 1) rmw(xa, ta);
+                if (on && rank == 1) rmw(xa, ta, w0);
                 if (__any_sync(0xffffffffu, rank >= 2)) {
                     __syncwarp();
-                    if (on && rank == 2) rmw(xa, ta);
+                    if (on && rank == 2) rmw(xa, ta, w0);
                     __syncwarp();
-                    if (on && rank == 3) rmw(xa, ta);
+                    if (on && rank == 3) rmw(xa, ta, w0);
                 }
                 __syncwarp();
             }
@@ -682,7 +719,8 @@ __device__ __noinline__ void step_finish(const TcParams &p, int st, uint8_t *sme
             (int)nthr, reinterpret_cast<double *>(smem + pl.off_pairs),
             [&] { bar_sync(kBarStep, nthr); },
             [&](int k, int c, float wf) {
-                *reinterpret_cast<float *>(img + img_offset(pl.Ntot, k, c)) = -2.0f * wf;
+                *reinterpret_cast<float *>(
+                    img + img_offset(lay_pack(pl.Ntot, pl.tail8 ? pl.nblkW - 1 : -1), k, c)) = -2.0f * wf;
             },
             [&](int k, int lane, double nrm2, bool neg) {
                 if (lane != 0) return;
@@ -848,9 +886,13 @@ bmu_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ T
             }
             if (elect_one()) {
                 mbar_arrive_expect_tx(bar_full + 8u * s, pl.stage_bytes);
-                for (int b = 0; b < pl.nblkX; ++b)
+                const int nfullb = pl.nblkX - pl.tail8;  // a tail8 block has its own tensor map
+                for (int b = 0; b < nfullb; ++b)
                     tma_load_2d(sbase + pl.off_x + s * pl.stage_bytes + (uint32_t)b * 16384u,
                                 &tmX, bar_full + 8u * s, b * 32, row0, kEvictFirst);
+                if (pl.tail8)
+                    tma_load_2d(sbase + pl.off_x + s * pl.stage_bytes + pl.x_tail_off, &p.tm_tail,
+                                bar_full + 8u * s, nfullb * 32, row0, kEvictFirst);
                 if (ptile >= 0)
                     for (int b = 0; b < pl.nblkX; ++b)
                         tma_prefetch_2d(&tmX, b * 32, (int32_t)(ptile * kTile));
@@ -904,11 +946,18 @@ bmu_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ T
                 if (elect_one()) {
                     const uint32_t d_tmem = tmem_base + buf * (uint32_t)NMMA;
                     const uint32_t wrow = (uint32_t)(c * NCHUNK) * 128u;
-                    for (int ks = 0; ks < pl.ksteps; ++ks) {
+                    const int kfull = pl.ksteps - pl.tail8;
+                    for (int ks = 0; ks < kfull; ++ks) {
                         const uint32_t blk = (uint32_t)(ks >> 2), ko = (uint32_t)(ks & 3) * 32u;
                         const uint64_t da = umma_desc_sw128(xs_addr + blk * 16384u + ko);
                         const uint64_t db = umma_desc_sw128(sbase + blk * wblk_bytes + wrow + ko);
                         mma_tf32(d_tmem, da, db, idesc, ks > 0 ? 1u : 0u);
+                    }
+                    if (pl.tail8) {  // the last K-step: 32-byte rows
+                        const uint64_t da = umma_desc_sw32(xs_addr + pl.x_tail_off);
+                        const uint64_t db =
+                            umma_desc_sw32(sbase + pl.w_tail_off + (uint32_t)(c * NCHUNK) * 32u);
+                        mma_tf32(d_tmem, da, db, idesc, 1u);
                     }
                     const uint64_t dbias = umma_desc_nosw(
                         sbase + pl.off_bias + (uint32_t)(c * NCHUNK / 8) * 256u, 128u, 256u);
@@ -970,6 +1019,7 @@ bmu_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ T
         uint32_t *pairs = reinterpret_cast<uint32_t *>(smem + pl.off_pairs) + warp * (2 * pair_cap);
         float *d2buf = reinterpret_cast<float *>(pairs + pair_cap);
         constexpr int Ntot = (NCH - 1) * NCHUNK + NMMA;
+        const int lay = lay_pack(Ntot, pl.tail8 ? pl.nblkX - 1 : -1);  // image / tile layout key
         const int nchunks16 = pl.C8 >> 2;    // 16-byte chunks holding real channels
         const float eps32 = (float)(pl.C + 8) * 2.4e-7f;
         const uint32_t tmem_lane = tmem_base + ((uint32_t)(quad * 32) << 16);
@@ -1018,10 +1068,22 @@ bmu_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ T
                 // chunk pc from every row would be an 8-way bank conflict).
                 uint32_t xaddr = sbase + pl.off_x + (uint32_t)s * pl.stage_bytes +
                                  (uint32_t)row * 128u + (r7 << 4);
-                for (int b = 0; b < pl.nblkX; ++b, xaddr += 16384u) {
+                for (int b = 0; b < pl.nblkX - pl.tail8; ++b, xaddr += 16384u) {
 #pragma unroll
                     for (uint32_t pc = 0; pc < 8; ++pc) {
                         const uint4 x = lds128(xaddr ^ (pc << 4));
+                        const uint64_t lo = pack2u(x.x, x.y), hi = pack2u(x.z, x.w);
+                        xa = fma2(lo, lo, xa);
+                        xb = fma2(hi, hi, xb);
+                        sgn |= (x.x | x.y) | (x.z | x.w);
+                    }
+                }
+                if (pl.tail8) {  // 32-byte rows: both chunks, either order
+                    const uint32_t ta = sbase + pl.off_x + (uint32_t)s * pl.stage_bytes +
+                                        pl.x_tail_off + (uint32_t)row * 32u;
+#pragma unroll
+                    for (uint32_t pc = 0; pc < 2; ++pc) {
+                        const uint4 x = lds128(ta + (pc << 4));
                         const uint64_t lo = pack2u(x.x, x.y), hi = pack2u(x.z, x.w);
                         xa = fma2(lo, lo, xa);
                         xb = fma2(hi, hi, xb);
@@ -1188,7 +1250,7 @@ bmu_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ T
                     if (c0 >= Ntot) c0 = 0;
                     if (c1 >= Ntot || c1 < 0) c1 = 0;
                     float d0, d1;
-                    duel_dist2_f32(xs, ws, Ntot, nchunks16, row, c0, c1, d0, d1);
+                    duel_dist2_f32(xs, ws, lay, nchunks16, row, c0, c1, d0, d1);
                     const float best = fminf(d0, d1);
                     const float bound = best * (1.0f + eps32) + 1.0e-30f;
                     ++st_flag;
@@ -1202,8 +1264,8 @@ bmu_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ T
                         ++st_fp64;
                         label = kLabelFixup;
                         if (c0 < pl.K && c1 < pl.K) {
-                            const double e0 = pair_dist_f64(xs, ws, Ntot, pl.C, row, c0);
-                            const double e1 = pair_dist_f64(xs, ws, Ntot, pl.C, row, c1);
+                            const double e0 = pair_dist_f64(xs, ws, lay, pl.C, row, c0);
+                            const double e1 = pair_dist_f64(xs, ws, lay, pl.C, row, c1);
                             label = (e1 < e0 ? c1 : c0) + 1;
                             if (!(e0 == e0) || !(e1 == e1)) label = kLabelFixup;
                         }
@@ -1250,7 +1312,7 @@ bmu_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ T
                     const int prow = (int)(pr >> 16) & 127;
                     int pnode = (int)(pr & 0xFFFFu);
                     if (pnode >= Ntot) pnode = 0;
-                    d2buf[pi] = pair_dist2_f32(xs, ws, Ntot, nchunks16, prow, pnode, (uint32_t)lane & 7u);
+                    d2buf[pi] = pair_dist2_f32(xs, ws, lay, nchunks16, prow, pnode, (uint32_t)lane & 7u);
                 }
                 __syncwarp();
                 if (flagged) {
@@ -1278,7 +1340,7 @@ bmu_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ T
                             if (!(d2buf[pbase + t] <= bound)) continue;
                             const int k = (int)(pairs[pbase + t] & 0xFFFFu);
                             if (k >= pl.K) continue;
-                            const double d = pair_dist_f64(xs, ws, Ntot, pl.C, row, k);
+                            const double d = pair_dist_f64(xs, ws, lay, pl.C, row, k);
                             if (d < bestd) {
                                 bestd = d;
                                 bestk = k;
@@ -1328,11 +1390,11 @@ bmu_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ T
                                 }
                             }
                         if (myk0 >= 0 && myk0 < pl.K) {
-                            mind = pair_dist_f64(xs, ws, Ntot, pl.C, frow, myk0);
+                            mind = pair_dist_f64(xs, ws, lay, pl.C, frow, myk0);
                             minid = myk0;
                         }
                         if (__any_sync(0xffffffffu, myk1 >= 0) && myk1 >= 0 && myk1 < pl.K) {
-                            const double d = pair_dist_f64(xs, ws, Ntot, pl.C, frow, myk1);
+                            const double d = pair_dist_f64(xs, ws, lay, pl.C, frow, myk1);
                             if (d < mind) {  // myk1 > myk0: strict < keeps the lower index on ties
                                 mind = d;
                                 minid = myk1;
@@ -1342,7 +1404,7 @@ bmu_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ T
                     }
                     if (!__any_sync(0xffffffffu, minid != 0x7fffffff)) {
                         for (int k = lane; k < pl.K; k += 32) {
-                            const double d = pair_dist_f64(xs, ws, Ntot, pl.C, frow, k);
+                            const double d = pair_dist_f64(xs, ws, lay, pl.C, frow, k);
                             if (d < mind) {
                                 mind = d;
                                 minid = k;

@@ -83,6 +83,25 @@ bool make_x_tensor_map(CUtensorMap *tm, const float *X, int64_t n, int C, int64_
     return true;
 }
 
+// plan.tail8: the last 8 channels of the K-steps as 32-byte rows (box 8 x 128, SWIZZLE_32B)
+bool make_x_tail_tensor_map(CUtensorMap *tm, const float *X, int64_t n, int C, int64_t ldX)
+{
+    EncodeTiledFn fn = get_encode_fn();
+    if (!fn) return false;
+    cuuint64_t gdim[2] = {(cuuint64_t)C, (cuuint64_t)n};
+    cuuint64_t gstride[1] = {(cuuint64_t)ldX * sizeof(float)};
+    cuuint32_t box[2] = {8u, (cuuint32_t)kTile};
+    cuuint32_t estr[2] = {1u, 1u};
+    CUresult r = fn(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float *>(X), gdim, gstride,
+                    box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_32B,
+                    CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) {
+        snprintf(g_last_error, sizeof(g_last_error), "cuTensorMapEncodeTiled (tail) failed: %d", (int)r);
+        return false;
+    }
+    return true;
+}
+
 int num_sms_current_device()
 {
     static int cached[64];
@@ -181,6 +200,8 @@ int bmu_tiles(const float *X, int64_t n, int C, int64_t ldX, const float *W, int
     bool use_tc = plan.ok && aligned && !(flags & PIXIE_FLAG_FORCE_EXACT);
     CUtensorMap tm;
     if (use_tc && !make_x_tensor_map(&tm, X, n, C, ldX)) use_tc = false;
+    CUtensorMap tm_tail = tm;
+    if (use_tc && plan.tail8 && !make_x_tail_tensor_map(&tm_tail, X, n, C, ldX)) use_tc = false;
     // control block: norms, flags, fix-up counter, grid-barrier words
     PX_CUDA(cudaMemsetAsync(ws.aux, 0, sizeof(CodebookAux), stream));
     if (!use_tc) {
@@ -210,6 +231,7 @@ int bmu_tiles(const float *X, int64_t n, int C, int64_t ldX, const float *W, int
         p.delta_scale = delta_scale_from_env();
         p.dbg_flags = getenv("PIXIE_DBG_FLAGS") ? atoi(getenv("PIXIE_DBG_FLAGS")) : 0;
         p.plan = plan;
+        p.tm_tail = tm_tail;
         if (fused) PX_CUDA(clear_group_tables(plan, ws, stream));
         if (plan.x3)
             PX_CUDA(launch_bmu_x3(tm, p, sum_parts(), stream));
@@ -528,6 +550,10 @@ static int launch_whole_pass(const float *X, int64_t n, int32_t C, int64_t ldX, 
     if (!make_x_tensor_map(&tm, empty ? ws.wimg : X, empty ? kTile : n, C,
                            empty ? (int64_t)(C + 3) / 4 * 4 : ldX))
         return PIXIE_ERR_UNSUPPORTED;
+    CUtensorMap tm_tail = tm;
+    if (plan.tail8 && !make_x_tail_tensor_map(&tm_tail, empty ? ws.wimg : X, empty ? kTile : n, C,
+                                              empty ? (int64_t)(C + 3) / 4 * 4 : ldX))
+        return PIXIE_ERR_UNSUPPORTED;
     if (world > 1) {
         const int len = K * (C + 1);
         const int grid = sum_parts();
@@ -587,6 +613,7 @@ static int launch_whole_pass(const float *X, int64_t n, int32_t C, int64_t ldX, 
     for (int r = 0; r < 8; ++r)
         p.peer_buf[r] = (world > 1 && r < world) ? reinterpret_cast<double *>(peer_bufs[r]) : nullptr;
     p.plan = plan;
+    p.tm_tail = tm_tail;
     PX_CUDA(clear_group_tables(plan, ws, st));
     PX_CUDA(launch_bmu_tc(tm, p, sum_parts(), st));
     return PIXIE_OK;

@@ -73,6 +73,14 @@ struct TcPlan {
     // split-operand assignment kernel (bmu_x3_kernel.cuh; make_x3_plan): the image holds a second
     // set of blocks with the low parts of -2 W at off_wlo, and every epilogue group owns a buffer
     // for the low parts of its next X tile at off_xl + g * stage_bytes
+    // tail8: C8 % 32 == 8 (C = 33..40, 65..72, 97..104) -- the last 32-channel block of the X tile
+    // and of the codebook image would be three quarters zero fill.  It is kept as 32-byte rows
+    // instead (one tf32 K-step per row, SWIZZLE_32B: 16-byte chunk c of row r at c ^ ((r >> 2) & 1)),
+    // loaded by a second tensor map: X stage = full blocks + 4 KiB at x_tail_off, image = full
+    // blocks + Ntot x 32 bytes at w_tail_off.  At C = 40, K = 400 (cfg3) that is 20 KiB instead of
+    // 32 per stage and 65 instead of 104 KiB of image: six pipeline stages instead of two.
+    int tail8;
+    uint32_t x_tail_off, w_tail_off;
     int x3;
     uint32_t off_wlo, off_xl;
     uint32_t smem_need;   // bytes used from the 1 KiB-aligned base (smem_bytes - alignment slack)
@@ -138,6 +146,7 @@ struct TcParams {
     int dbg_flags;         // experiments (PIXIE_DBG_FLAGS); 4 = per-step printf in PIXIE_PROFILE builds, 8 = no L2 prefetch
     float delta_scale;     // 1 in production; tests shrink the candidate window to probe its margin
     TcPlan plan;
+    alignas(64) CUtensorMap tm_tail;  // plan.tail8: channels 32 (nblk - 1) .. + 7, box 8 x 128, SWIZZLE_32B
 };
 
 // launchers (each enqueues on `stream` and returns the cudaError_t of the launch)

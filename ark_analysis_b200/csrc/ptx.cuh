@@ -338,6 +338,13 @@ __device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t smem_addr)
     return static_cast<uint64_t>((smem_addr & 0x3FFFFu) >> 4) | (1ull << 16) |
            (static_cast<uint64_t>(1024 >> 4) << 32) | (1ull << 46) | (2ull << 61);
 }
+// K-major operand tile with 32-byte rows (ONE tf32 K-step per row), SWIZZLE_32B (Swizzle<1,4,3>):
+// 8-row groups are 256 bytes apart (SBO).
+__device__ __forceinline__ uint64_t umma_desc_sw32(uint32_t smem_addr)
+{
+    return static_cast<uint64_t>((smem_addr & 0x3FFFFu) >> 4) | (1ull << 16) |
+           (static_cast<uint64_t>(256 >> 4) << 32) | (1ull << 46) | (6ull << 61);
+}
 // K-major, no swizzle ("interleave"): 8x16-byte core matrices; lbo = byte distance between the two
 // K-adjacent core matrices of one MMA, sbo = byte distance between 8-row groups.
 __device__ __forceinline__ uint64_t umma_desc_nosw(uint32_t smem_addr, uint32_t lbo, uint32_t sbo)
