@@ -155,7 +155,7 @@ TcPlan make_tc_plan(int C, int K, bool acc)
             // carve-out -> 28 KB) thrashes on it.  A pipeline one tile per group deep is enough here
             // (the producer runs a whole step ahead anyway), so stay under the 164 KB carve-out
             // when that is possible: cfg2 8 -> 4 stages, training pass 1.72 -> 1.56 ms.
-            const uint32_t soft = 164u * 1024u - 1024u;
+            const uint32_t soft = env_int("PIXIE_TC_SOFTCAP", 1) ? 164u * 1024u - 1024u : limit;  // 0: experiments
             while (p.nstage > v.NG && p.off_x + scratch + (uint32_t)p.nstage * p.stage_bytes > soft)
                 p.nstage -= v.NG;
         }

@@ -1389,18 +1389,45 @@ bmu_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ T
                                     ++rank;
                                 }
                             }
-                        if (myk0 >= 0 && myk0 < pl.K) {
-                            mind = pair_dist_f64(xs, ws, lay, pl.C, frow, myk0);
-                            minid = myk0;
-                        }
-                        if (__any_sync(0xffffffffu, myk1 >= 0) && myk1 >= 0 && myk1 < pl.K) {
-                            const double d = pair_dist_f64(xs, ws, lay, pl.C, frow, myk1);
-                            if (d < mind) {  // myk1 > myk0: strict < keeps the lower index on ties
-                                mind = d;
-                                minid = myk1;
+                        // fp32 first (stage 2 of the row, a candidate per lane): only the nodes
+                        // within the fp32 error of the smallest distance can be the minimum.  In
+                        // the first pass from a sampled codebook (hundreds of nodes drawn from a
+                        // few dozen populations) nearly every row comes through here with 20+
+                        // candidates whose distances differ in the second digit: one survivor,
+                        // no fp64 at all (it used to be an fp64 distance per candidate: 10 us per
+                        // K = 400 tile, a third of the training pass).
+                        const bool v0 = myk0 >= 0 && myk0 < pl.K, v1 = myk1 >= 0 && myk1 < pl.K;
+                        float f0 = __int_as_float(0x7f800000), f1 = f0;
+                        if (v0) f0 = pair_dist2_f32(xs, ws, lay, nchunks16, frow, myk0, (uint32_t)lane & 7u);
+                        if (__any_sync(0xffffffffu, v1) && v1)
+                            f1 = pair_dist2_f32(xs, ws, lay, nchunks16, frow, myk1, (uint32_t)lane & 7u);
+                        float best = fminf(f0, f1);
+                        for (int o = 16; o > 0; o >>= 1)
+                            best = fminf(best, __shfl_xor_sync(0xffffffffu, best, o));
+                        const float bound = best * (1.0f + eps32) + 1.0e-30f;
+                        const bool s0 = v0 && f0 <= bound, s1 = v1 && f1 <= bound;
+                        const unsigned b0 = __ballot_sync(0xffffffffu, s0);
+                        const unsigned b1 = __ballot_sync(0xffffffffu, s1);
+                        const int nsurv = __popc(b0) + __popc(b1);
+                        if (nsurv == 1) {
+                            const int wl = b0 ? __ffs(b0) - 1 : __ffs(b1) - 1;
+                            minid = __shfl_sync(0xffffffffu, b0 ? myk0 : myk1, wl);
+                            mind = 0.0;  // every lane agrees: the reduction below returns minid
+                        } else if (nsurv >= 2) {
+                            // stage 3 over the survivors: the reference's own fp64 sequence
+                            if (s0) {
+                                mind = pair_dist_f64(xs, ws, lay, pl.C, frow, myk0);
+                                minid = myk0;
                             }
-                        }
-                        if (!(mind == mind)) mind = DBL_MAX, minid = 0x7fffffff;
+                            if (s1) {
+                                const double d = pair_dist_f64(xs, ws, lay, pl.C, frow, myk1);
+                                if (d < mind) {  // myk1 > myk0: strict < keeps the lower index on ties
+                                    mind = d;
+                                    minid = myk1;
+                                }
+                            }
+                            if (!(mind == mind)) mind = DBL_MAX, minid = 0x7fffffff;
+                        }  // no survivor (every distance NaN): the full loop below
                     }
                     if (!__any_sync(0xffffffffu, minid != 0x7fffffff)) {
                         for (int k = lane; k < pl.K; k += 32) {
