@@ -96,7 +96,10 @@ TcPlan make_tc_plan(int C, int K, bool acc)
         if (need > 512) continue;
         p.tmem_cols = 32;
         while (p.tmem_cols < need) p.tmem_cols *= 2;
-        p.tail8 = (p.C8 % 32 == 8 && p.nblkX >= 2 && p.nblkX == p.nblkW &&
+        // (assignment only: in train mode the stage count stays at one per group anyway -- the
+        // L1 carve-out rule below -- and the tail8 code paths cost the fused kernel more than the
+        // smaller tiles bring: cfg3 shard pass 22.6 ms without, 22.8 ms with, same box)
+        p.tail8 = (!acc && p.C8 % 32 == 8 && p.nblkX >= 2 && p.nblkX == p.nblkW &&
                    env_int("PIXIE_TAIL8", 1) != 0) ? 1 : 0;
         p.stage_bytes = (uint32_t)p.nblkX * 16384u;
         p.off_bias = (uint32_t)p.nblkW * (uint32_t)p.Ntot * 128u;

@@ -1,5 +1,6 @@
 // bmu_tc_inst_acc.cu -- instantiates the ACC=true family of bmu_tc_kernel.
 #define PIXIE_FAMILY_ACC true
+#define PIXIE_FAMILY_NO_T8 1
 #include "bmu_tc_kernel.cuh"
 
 namespace pixie {

@@ -97,20 +97,22 @@ __host__ __device__ __forceinline__ uint32_t bias_offset(int row, int col)
 // ------------------------------------------------------------------------------------------------
 // Both the X stages (written by TMA SWIZZLE_128B) and the codebook image keep logical 16-byte
 // chunk c of row r of a 32-column block at physical chunk (c ^ (r & 7)).
+template <bool T8>
 __device__ __forceinline__ const float4 *x_chunk_ptr(const uint8_t *xs, int lay, int row, int blk,
                                                      int chunk)
 {
-    if (blk == (lay >> 16) - 1)
+    if (T8 && blk == (lay >> 16) - 1)
         return reinterpret_cast<const float4 *>(xs + (size_t)blk * 16384u + (size_t)row * 32u +
                                                 (size_t)(((chunk ^ (row >> 2)) & 1) << 4));
     return reinterpret_cast<const float4 *>(xs + (size_t)blk * 16384u + (size_t)row * 128u +
                                             (size_t)(((chunk ^ (row & 7)) & 7) << 4));
 }
+template <bool T8>
 __device__ __forceinline__ const float4 *w_chunk_ptr(const uint8_t *ws, int lay, int node, int blk,
                                                      int chunk)
 {
     const int Ntot = lay & 0xFFFF;
-    if (blk == (lay >> 16) - 1)
+    if (T8 && blk == (lay >> 16) - 1)
         return reinterpret_cast<const float4 *>(ws + (size_t)blk * (size_t)Ntot * 128u +
                                                 (size_t)node * 32u +
                                                 (size_t)(((chunk ^ (node >> 2)) & 1) << 4));
@@ -137,6 +139,7 @@ __device__ __forceinline__ void dist2_chunk(const float4 x, const float4 w, uint
 // DIFFERENT rows, and chunk pc of eight different rows is one 16-byte bank group -- an 8-way
 // conflict -- while chunks pc ^ rot spread a quarter-warp over all eight groups.
 // The last, partial block is walked logically so the bias columns of the image are never read.
+template <bool T8 = false>
 __device__ __forceinline__ float pair_dist2_f32(const uint8_t *xs, const uint8_t *ws, int lay,
                                                 int nchunks16, int row, int node, uint32_t rot)
 {
@@ -164,8 +167,8 @@ __device__ __forceinline__ float pair_dist2_f32(const uint8_t *xs, const uint8_t
     }
     const int rem = nchunks16 & 7;
     for (int lc = 0; lc < rem; ++lc) {
-        const float4 x = *x_chunk_ptr(xs, lay, row, nfull, lc);
-        const float4 w = *w_chunk_ptr(ws, lay, node, nfull, lc);
+        const float4 x = *x_chunk_ptr<T8>(xs, lay, row, nfull, lc);
+        const float4 w = *w_chunk_ptr<T8>(ws, lay, node, nfull, lc);
         dist2_chunk(x, w, half2, acc0, acc1);
     }
     float a, b, c, d;
@@ -178,12 +181,13 @@ __device__ __forceinline__ float pair_dist2_f32(const uint8_t *xs, const uint8_t
 // one walk over the row (the common case: a flagged row has exactly two candidates).  The thread
 // reads ITS OWN row, chunk c at physical chunk c ^ (row & 7), so a quarter-warp (8 consecutive
 // rows) covers all eight bank groups; codebook chunks follow the same logical order.
+template <bool T8 = false>
 __device__ __forceinline__ void duel_dist2_f32(const uint8_t *xs, const uint8_t *ws, int lay,
                                                int nchunks16, int row, int na, int nb, float &da,
                                                float &db)
 {
     const int Ntot = lay & 0xFFFF;
-    const bool tail = (lay >> 16) != 0;
+    constexpr bool tail = T8;
     const uint64_t half2 = pack2(0.5f, 0.5f);
     uint64_t a0 = 0ull, a1 = 0ull, b0 = 0ull, b1 = 0ull;
     // rows are 128-byte aligned: OR the row's swizzle key in, XOR the logical chunk index
@@ -244,14 +248,15 @@ __device__ __forceinline__ void duel_dist2_f32(const uint8_t *xs, const uint8_t 
 // stage 3: the reference's fp64 operation sequence for one (row, node) pair
 // (oracle/pixie_oracle.c nearest_node): tmp = x - w; acc = acc + tmp * tmp (separately rounded),
 // in channel order; d = sqrt(acc).
+template <bool T8 = false>
 static __device__ __noinline__ double pair_dist_f64(const uint8_t *xs, const uint8_t *ws, int lay, int C,
                                              int row, int node)
 {
     double acc = 0.0;
     for (int j = 0; j < C; ++j) {
         const int blk = j >> 5, cc = j & 31;
-        const float xf = reinterpret_cast<const float *>(x_chunk_ptr(xs, lay, row, blk, cc >> 2))[cc & 3];
-        const float wf = reinterpret_cast<const float *>(w_chunk_ptr(ws, lay, node, blk, cc >> 2))[cc & 3];
+        const float xf = reinterpret_cast<const float *>(x_chunk_ptr<T8>(xs, lay, row, blk, cc >> 2))[cc & 3];
+        const float wf = reinterpret_cast<const float *>(w_chunk_ptr<T8>(ws, lay, node, blk, cc >> 2))[cc & 3];
         const double tmp = __dsub_rn((double)xf, (double)(-0.5f * wf));
         acc = __dadd_rn(acc, __dmul_rn(tmp, tmp));
     }
@@ -356,7 +361,7 @@ __device__ __forceinline__ void publish_labels(uint8_t *smem, uint32_t lab_off, 
     bar_sync(1u + (uint32_t)g, 128);
 }
 
-template <int NBLK, bool TABG>
+template <int NBLK, bool TABG, bool T8>
 __device__ __noinline__ void tile_accumulate_blk(const TcParams &p, uint8_t *smem,
                                                     uint32_t xs_addr, uint32_t tab_addr,
                                                     float *tab_g, uint32_t lab_off,
@@ -401,7 +406,7 @@ __device__ __noinline__ void tile_accumulate_blk(const TcParams &p, uint8_t *sme
     const uint32_t my = list_addr + r4 * 8u;
     // source of chunk ck of a row in block blk; a tail8 block keeps 32-byte rows (row = w0 >> 7,
     // chunk ck at ck ^ ((row >> 2) & 1); only ck < 2 gets here: last_ok)
-    const bool t8 = pl.tail8 != 0;
+    constexpr bool t8 = T8;
     const uint32_t XT = xs_addr + pl.x_tail_off;
     auto xsrc = [&](uint32_t xa, uint32_t w0, int blk) -> uint32_t {
         if (t8 && blk == NBLK - 1) return XT + ((w0 >> 7) << 5) + (((ck ^ (w0 >> 9)) & 1u) << 4);
@@ -482,6 +487,7 @@ __device__ __noinline__ void tile_accumulate_blk(const TcParams &p, uint8_t *sme
     __syncwarp();  // the list is the warp's pair buffer again from the next tile on
 }
 
+template <bool T8>
 __device__ __forceinline__ void tile_accumulate(const TcParams &p, uint8_t *smem, uint32_t xs_addr,
                                                 uint32_t tab_addr, float *tab_g, uint32_t lab_off,
                                                 uint32_t list_addr, int quad, int lane,
@@ -491,10 +497,10 @@ __device__ __forceinline__ void tile_accumulate(const TcParams &p, uint8_t *smem
 #define PIXIE_ACC_CASE(n_)                                                                        \
     case n_:                                                                                      \
         if (tab_g != nullptr)                                                                     \
-            tile_accumulate_blk<n_, true>(p, smem, xs_addr, tab_addr, tab_g, lab_off, list_addr,  \
+            tile_accumulate_blk<n_, true, T8>(p, smem, xs_addr, tab_addr, tab_g, lab_off, list_addr,  \
                                           quad, lane, parity);                                    \
         else                                                                                      \
-            tile_accumulate_blk<n_, false>(p, smem, xs_addr, tab_addr, tab_g, lab_off, list_addr, \
+            tile_accumulate_blk<n_, false, T8>(p, smem, xs_addr, tab_addr, tab_g, lab_off, list_addr, \
                                            quad, lane, parity);                                   \
         break;
     switch (p.plan.nblkX) {
@@ -758,7 +764,11 @@ __device__ __noinline__ void step_finish(const TcParams &p, int st, uint8_t *sme
 // ------------------------------------------------------------------------------------------------
 // the kernel
 // ------------------------------------------------------------------------------------------------
-template <int SL, int SPC, int NCH, int NG, bool ACC>
+// T8: the plan's "tail8" layout (TcPlan::tail8) as a compile-time switch -- as a run-time flag its
+// branches and the extra live values cost the 96-register epilogue of every OTHER shape 7 % (cfg2
+// assign 1.85 -> 1.98 ms, same box), so shapes without a tail block run instantiations that do
+// not contain it.
+template <int SL, int SPC, int NCH, int NG, bool ACC, bool T8 = false>
 __global__ void __launch_bounds__(NG * 128 + 64, 1)
 bmu_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ TcParams p)
 {
@@ -886,11 +896,11 @@ bmu_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ T
             }
             if (elect_one()) {
                 mbar_arrive_expect_tx(bar_full + 8u * s, pl.stage_bytes);
-                const int nfullb = pl.nblkX - pl.tail8;  // a tail8 block has its own tensor map
+                const int nfullb = pl.nblkX - (T8 ? 1 : 0);  // a tail8 block has its own tensor map
                 for (int b = 0; b < nfullb; ++b)
                     tma_load_2d(sbase + pl.off_x + s * pl.stage_bytes + (uint32_t)b * 16384u,
                                 &tmX, bar_full + 8u * s, b * 32, row0, kEvictFirst);
-                if (pl.tail8)
+                if constexpr (T8)
                     tma_load_2d(sbase + pl.off_x + s * pl.stage_bytes + pl.x_tail_off, &p.tm_tail,
                                 bar_full + 8u * s, nfullb * 32, row0, kEvictFirst);
                 if (ptile >= 0)
@@ -946,14 +956,14 @@ bmu_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ T
                 if (elect_one()) {
                     const uint32_t d_tmem = tmem_base + buf * (uint32_t)NMMA;
                     const uint32_t wrow = (uint32_t)(c * NCHUNK) * 128u;
-                    const int kfull = pl.ksteps - pl.tail8;
+                    const int kfull = pl.ksteps - (T8 ? 1 : 0);
                     for (int ks = 0; ks < kfull; ++ks) {
                         const uint32_t blk = (uint32_t)(ks >> 2), ko = (uint32_t)(ks & 3) * 32u;
                         const uint64_t da = umma_desc_sw128(xs_addr + blk * 16384u + ko);
                         const uint64_t db = umma_desc_sw128(sbase + blk * wblk_bytes + wrow + ko);
                         mma_tf32(d_tmem, da, db, idesc, ks > 0 ? 1u : 0u);
                     }
-                    if (pl.tail8) {  // the last K-step: 32-byte rows
+                    if constexpr (T8) {  // the last K-step: 32-byte rows
                         const uint64_t da = umma_desc_sw32(xs_addr + pl.x_tail_off);
                         const uint64_t db =
                             umma_desc_sw32(sbase + pl.w_tail_off + (uint32_t)(c * NCHUNK) * 32u);
@@ -1019,7 +1029,7 @@ bmu_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ T
         uint32_t *pairs = reinterpret_cast<uint32_t *>(smem + pl.off_pairs) + warp * (2 * pair_cap);
         float *d2buf = reinterpret_cast<float *>(pairs + pair_cap);
         constexpr int Ntot = (NCH - 1) * NCHUNK + NMMA;
-        const int lay = lay_pack(Ntot, pl.tail8 ? pl.nblkX - 1 : -1);  // image / tile layout key
+        const int lay = T8 ? lay_pack(Ntot, pl.nblkX - 1) : Ntot;  // image / tile layout key
         const int nchunks16 = pl.C8 >> 2;    // 16-byte chunks holding real channels
         const float eps32 = (float)(pl.C + 8) * 2.4e-7f;
         const uint32_t tmem_lane = tmem_base + ((uint32_t)(quad * 32) << 16);
@@ -1068,7 +1078,7 @@ bmu_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ T
                 // chunk pc from every row would be an 8-way bank conflict).
                 uint32_t xaddr = sbase + pl.off_x + (uint32_t)s * pl.stage_bytes +
                                  (uint32_t)row * 128u + (r7 << 4);
-                for (int b = 0; b < pl.nblkX - pl.tail8; ++b, xaddr += 16384u) {
+                for (int b = 0; b < pl.nblkX - (T8 ? 1 : 0); ++b, xaddr += 16384u) {
 #pragma unroll
                     for (uint32_t pc = 0; pc < 8; ++pc) {
                         const uint4 x = lds128(xaddr ^ (pc << 4));
@@ -1078,7 +1088,7 @@ bmu_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ T
                         sgn |= (x.x | x.y) | (x.z | x.w);
                     }
                 }
-                if (pl.tail8) {  // 32-byte rows: both chunks, either order
+                if constexpr (T8) {  // 32-byte rows: both chunks, either order
                     const uint32_t ta = sbase + pl.off_x + (uint32_t)s * pl.stage_bytes +
                                         pl.x_tail_off + (uint32_t)row * 32u;
 #pragma unroll
@@ -1250,7 +1260,7 @@ bmu_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ T
                     if (c0 >= Ntot) c0 = 0;
                     if (c1 >= Ntot || c1 < 0) c1 = 0;
                     float d0, d1;
-                    duel_dist2_f32(xs, ws, lay, nchunks16, row, c0, c1, d0, d1);
+                    duel_dist2_f32<T8>(xs, ws, lay, nchunks16, row, c0, c1, d0, d1);
                     const float best = fminf(d0, d1);
                     const float bound = best * (1.0f + eps32) + 1.0e-30f;
                     ++st_flag;
@@ -1264,8 +1274,8 @@ bmu_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ T
                         ++st_fp64;
                         label = kLabelFixup;
                         if (c0 < pl.K && c1 < pl.K) {
-                            const double e0 = pair_dist_f64(xs, ws, lay, pl.C, row, c0);
-                            const double e1 = pair_dist_f64(xs, ws, lay, pl.C, row, c1);
+                            const double e0 = pair_dist_f64<T8>(xs, ws, lay, pl.C, row, c0);
+                            const double e1 = pair_dist_f64<T8>(xs, ws, lay, pl.C, row, c1);
                             label = (e1 < e0 ? c1 : c0) + 1;
                             if (!(e0 == e0) || !(e1 == e1)) label = kLabelFixup;
                         }
@@ -1312,7 +1322,7 @@ bmu_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ T
                     const int prow = (int)(pr >> 16) & 127;
                     int pnode = (int)(pr & 0xFFFFu);
                     if (pnode >= Ntot) pnode = 0;
-                    d2buf[pi] = pair_dist2_f32(xs, ws, lay, nchunks16, prow, pnode, (uint32_t)lane & 7u);
+                    d2buf[pi] = pair_dist2_f32<T8>(xs, ws, lay, nchunks16, prow, pnode, (uint32_t)lane & 7u);
                 }
                 __syncwarp();
                 if (flagged) {
@@ -1340,7 +1350,7 @@ bmu_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ T
                             if (!(d2buf[pbase + t] <= bound)) continue;
                             const int k = (int)(pairs[pbase + t] & 0xFFFFu);
                             if (k >= pl.K) continue;
-                            const double d = pair_dist_f64(xs, ws, lay, pl.C, row, k);
+                            const double d = pair_dist_f64<T8>(xs, ws, lay, pl.C, row, k);
                             if (d < bestd) {
                                 bestd = d;
                                 bestk = k;
@@ -1398,9 +1408,9 @@ bmu_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ T
                         // K = 400 tile, a third of the training pass).
                         const bool v0 = myk0 >= 0 && myk0 < pl.K, v1 = myk1 >= 0 && myk1 < pl.K;
                         float f0 = __int_as_float(0x7f800000), f1 = f0;
-                        if (v0) f0 = pair_dist2_f32(xs, ws, lay, nchunks16, frow, myk0, (uint32_t)lane & 7u);
+                        if (v0) f0 = pair_dist2_f32<T8>(xs, ws, lay, nchunks16, frow, myk0, (uint32_t)lane & 7u);
                         if (__any_sync(0xffffffffu, v1) && v1)
-                            f1 = pair_dist2_f32(xs, ws, lay, nchunks16, frow, myk1, (uint32_t)lane & 7u);
+                            f1 = pair_dist2_f32<T8>(xs, ws, lay, nchunks16, frow, myk1, (uint32_t)lane & 7u);
                         float best = fminf(f0, f1);
                         for (int o = 16; o > 0; o >>= 1)
                             best = fminf(best, __shfl_xor_sync(0xffffffffu, best, o));
@@ -1416,11 +1426,11 @@ bmu_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ T
                         } else if (nsurv >= 2) {
                             // stage 3 over the survivors: the reference's own fp64 sequence
                             if (s0) {
-                                mind = pair_dist_f64(xs, ws, lay, pl.C, frow, myk0);
+                                mind = pair_dist_f64<T8>(xs, ws, lay, pl.C, frow, myk0);
                                 minid = myk0;
                             }
                             if (s1) {
-                                const double d = pair_dist_f64(xs, ws, lay, pl.C, frow, myk1);
+                                const double d = pair_dist_f64<T8>(xs, ws, lay, pl.C, frow, myk1);
                                 if (d < mind) {  // myk1 > myk0: strict < keeps the lower index on ties
                                     mind = d;
                                     minid = myk1;
@@ -1431,7 +1441,7 @@ bmu_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ T
                     }
                     if (!__any_sync(0xffffffffu, minid != 0x7fffffff)) {
                         for (int k = lane; k < pl.K; k += 32) {
-                            const double d = pair_dist_f64(xs, ws, lay, pl.C, frow, k);
+                            const double d = pair_dist_f64<T8>(xs, ws, lay, pl.C, frow, k);
                             if (d < mind) {
                                 mind = d;
                                 minid = k;
@@ -1483,7 +1493,7 @@ bmu_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ T
                                lane, (grow < p.n && label > 0) ? label - 1 : pl.K, use & 1u);
                 PIXIE_TOCK(7);
                 PIXIE_TRACE(7, seq);
-                tile_accumulate(p, smem, sbase + pl.off_x + (uint32_t)s * pl.stage_bytes,
+                tile_accumulate<T8>(p, smem, sbase + pl.off_x + (uint32_t)s * pl.stage_bytes,
                                 smem_u32(tab_s), tab_g, pl.off_lab + (uint32_t)g * 512u,
                                 smem_u32(pairs), quad, lane, use & 1u);
             }
@@ -1538,12 +1548,12 @@ bmu_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ T
     }
 }
 
-template <int SL, int SPC, int NCH, int NG, bool ACC>
+template <int SL, int SPC, int NCH, int NG, bool ACC, bool T8>
 static cudaError_t launch_variant(const CUtensorMap &tmX, const TcParams &p, int grid,
                                   cudaStream_t stream)
 {
     constexpr int kThreads = NG * 128 + 64;
-    cudaError_t e = cudaFuncSetAttribute(bmu_tc_kernel<SL, SPC, NCH, NG, ACC>,
+    cudaError_t e = cudaFuncSetAttribute(bmu_tc_kernel<SL, SPC, NCH, NG, ACC, T8>,
                                          cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          (int)p.plan.smem_bytes);
     if (e != cudaSuccess) return e;
@@ -1552,22 +1562,31 @@ static cudaError_t launch_variant(const CUtensorMap &tmX, const TcParams &p, int
         // guarantees (or refuses) co-residency of all CTAs
         void *args[] = {const_cast<CUtensorMap *>(&tmX), const_cast<TcParams *>(&p)};
         e = cudaLaunchCooperativeKernel(
-            reinterpret_cast<const void *>(&bmu_tc_kernel<SL, SPC, NCH, NG, ACC>),
+            reinterpret_cast<const void *>(&bmu_tc_kernel<SL, SPC, NCH, NG, ACC, T8>),
             dim3(grid), dim3(kThreads), args, p.plan.smem_bytes, stream);
         count_launch();
         return e;
     } else {
-        bmu_tc_kernel<SL, SPC, NCH, NG, ACC>
+        bmu_tc_kernel<SL, SPC, NCH, NG, ACC, T8>
             <<<grid, kThreads, p.plan.smem_bytes, stream>>>(tmX, p);
         count_launch();
         return cudaGetLastError();
     }
 }
 
-// Body of a variant family's launcher: dispatch on the plan's template parameters.
+// Body of a variant family's launcher: dispatch on the plan's template parameters.  Only the plain
+// (assignment) family has tail8 instantiations: make_tc_plan() never sets tail8 for train-mode plans.
+#ifdef PIXIE_FAMILY_NO_T8
+#define PIXIE_LAUNCH_T8(a_, b_, c_, d_) \
+    launch_variant<a_, b_, c_, d_, PIXIE_FAMILY_ACC, false>(tmX, p, grid, stream)
+#else
+#define PIXIE_LAUNCH_T8(a_, b_, c_, d_)                                                            \
+    (pl.tail8 ? launch_variant<a_, b_, c_, d_, PIXIE_FAMILY_ACC, true>(tmX, p, grid, stream)      \
+              : launch_variant<a_, b_, c_, d_, PIXIE_FAMILY_ACC, false>(tmX, p, grid, stream))
+#endif
 #define PIXIE_VARIANT(a_, b_, c_, d_)                               \
     if (pl.SL == a_ && pl.spc == b_ && pl.NCH == c_ && pl.NG == d_) \
-        return launch_variant<a_, b_, c_, d_, PIXIE_FAMILY_ACC>(tmX, p, grid, stream);
+        return PIXIE_LAUNCH_T8(a_, b_, c_, d_);
 #define PIXIE_ALL_VARIANTS     \
     PIXIE_VARIANT(32, 1, 1, 4) \
     PIXIE_VARIANT(32, 2, 1, 4) \
