@@ -22,7 +22,7 @@ STAT_ROWS_FLAGGED, STAT_PAIRS, STAT_ROWS_FP64, STAT_ROWS_FIXUP, STAT_KERNEL = 0,
 
 # every symbol include/pixie_b200.h declares (checked by tests/test_capi_symbols.py)
 SYMBOLS = [
-    "pixie_version", "pixie_error_string", "pixie_kernel_launches", "pixie_device_count", "pixie_debug_trace", "pixie_workspace_bytes",
+    "pixie_version", "pixie_error_string", "pixie_kernel_launches", "pixie_device_count", "pixie_debug_trace", "pixie_plan_describe", "pixie_workspace_bytes",
     "pixie_bmu_f32", "pixie_bmu_dist_f64", "pixie_cluster_sums_f32", "pixie_columns_to_rows_f32", "pixie_som_online_f64", "pixie_libc_sample_indices",
     "pixie_som_accum_f32", "pixie_som_apply_f64",
     "pixie_som_train_f32", "pixie_peer_buffer_bytes", "pixie_som_train_peers_supported",
@@ -79,6 +79,9 @@ def lib():
         L.pixie_error_string.restype = c.c_char_p
         L.pixie_error_string.argtypes = [c.c_int]
         L.pixie_device_count.restype = c.c_int
+        if hasattr(L, "pixie_plan_describe"):
+            L.pixie_plan_describe.restype = c.c_int
+            L.pixie_plan_describe.argtypes = [i32, i32, i32, vp]
         if hasattr(L, "pixie_debug_trace"):  # absent from older builds loaded via PIXIE_LIB_PATH
             L.pixie_debug_trace.restype = c.c_int
             L.pixie_debug_trace.argtypes = [vp, c.c_int]

@@ -303,6 +303,22 @@ int pixie_debug_trace(unsigned long long *out_host, int max_events)
 #endif
 }
 
+int pixie_plan_describe(int32_t C, int32_t K, int32_t train, int32_t *out_host)
+{
+    if (!out_host || C < 1 || K < 1) return PIXIE_ERR_INVALID_ARG;
+    TcPlan plan = make_tc_plan(C, K, train != 0);
+    if (!train) {
+        const TcPlan x3 = make_x3_plan(C, K);
+        if (x3.ok) plan = x3;
+    }
+    const int32_t v[16] = {plan.ok ? 1 : 0, plan.x3, plan.SL, plan.spc, plan.NCH, plan.NG,
+                           plan.nstage, (int32_t)plan.stage_bytes, (int32_t)plan.smem_bytes,
+                           (int32_t)plan.wimg_bytes, plan.tmem_cols, plan.tail8, plan.tab_global,
+                           plan.Nmma, plan.Ntot, plan.ksteps};
+    for (int i = 0; i < 16; ++i) out_host[i] = plan.ok ? v[i] : 0;
+    return PIXIE_OK;
+}
+
 int pixie_device_count(void)
 {
     int n = 0;

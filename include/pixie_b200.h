@@ -62,6 +62,17 @@ int pixie_device_count(void);
  * always 0 in the production build. */
 int pixie_debug_trace(unsigned long long *out_host, int max_events);
 
+/* Which kernel and shared-memory layout the library would use for a (C, K) codebook: pure host
+ * logic, no device needed (the CPU test-suite checks the planner with it).  train != 0: the plan of
+ * the fused training kernel, else of assignment.  Writes up to 16 int32 to out:
+ *   [0] 1 = a tensor-core plan exists   [1] kernel: 0 plain, 1 split-operand (3 x tf32)
+ *   [2] SL  [3] slices per chunk  [4] accumulator chunks per tile  [5] epilogue groups
+ *   [6] X pipeline stages  [7] bytes per stage  [8] dynamic shared memory requested
+ *   [9] codebook image bytes  [10] TMEM columns  [11] tail8 layout  [12] sum tables in global memory
+ *   [13] MMA N  [14] image rows per block  [15] K-steps
+ * Returns PIXIE_OK or PIXIE_ERR_INVALID_ARG. */
+int pixie_plan_describe(int32_t C, int32_t K, int32_t train, int32_t *out_host);
+
 /* Bytes of device workspace pixie_bmu_f32 / pixie_som_accum_f32 need for these shapes. */
 size_t pixie_workspace_bytes(int64_t n, int32_t C, int32_t K);
 
