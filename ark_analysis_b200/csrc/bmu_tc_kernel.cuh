@@ -1127,6 +1127,77 @@ bmu_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ T
 #pragma unroll
                 for (int w = 0; w < NW; ++w) mw[a][w] = 0u;
 
+            if constexpr (NCH == 2 && !ACC && T8) {
+                // K > 256 with a tail block (cfg3: 40 channels, 20 x 20): the four slices of a
+                // tile as ONE loop body instead of four unrolled copies.  The unrolled stream of
+                // this instantiation is ~2000 instructions (32 KB) per tile, more than the 32 KB
+                // instruction cache behind the L0s holds: its hit rate was 79 % and
+                // instruction-fetch stalls 17 % of the epilogue warps' time (profiles/r02_notes.md
+                // section 12).  The masks of the slice in hand live in cur[] and are committed to
+                // mw[sl] by a chain of selects (register arrays need static indices).  Measured:
+                // C = 40 5.02 -> 4.86 ms; without a tail block the rolled loop LOSES (C = 16
+                // 1.20 -> 1.28 ms, C = 64 1.57 -> 1.59 ms), so those keep the unrolled form.
+#pragma unroll 1
+                for (int sl = 0; sl < NS; ++sl) {
+                    const int c = sl / SPC, sidx = sl - c * SPC;
+                    const uint32_t q = seq * 2u + (uint32_t)c;  // chunk counter; buffers alternate
+                    const uint32_t buf = q & 1u, bph = (q >> 1) & 1u;
+                    if (sidx == 0) {
+                        // (see below: the previous use's release pins the barrier's phase)
+                        if (q >= 2) mbar_wait(bar_tempty + 8u * buf, bph ^ 1u);
+                        mbar_wait(bar_tfull + 8u * buf, bph);
+                        tc_fence_after();
+                    }
+                    uint32_t vr[SL];
+                    tmem_ld_cols<SL>(tmem_lane + buf * (uint32_t)NMMA + (uint32_t)(sidx * SL), vr);
+                    tc_wait_ld();
+                    if (sidx == SPC - 1) {
+                        tc_fence_before();
+                        __syncwarp();
+                        if (lane == 0) mbar_arrive(bar_tempty + 8u * buf);
+                    }
+                    float a0 = __uint_as_float(vr[0]), a1 = __uint_as_float(vr[1]);
+                    float a2 = __uint_as_float(vr[2]), a3 = __uint_as_float(vr[3]);
+#pragma unroll
+                    for (int i = 4; i + 7 < SL; i += 8) {
+                        a0 = fminf(fminf(a0, __uint_as_float(vr[i])), __uint_as_float(vr[i + 4]));
+                        a1 = fminf(fminf(a1, __uint_as_float(vr[i + 1])), __uint_as_float(vr[i + 5]));
+                        a2 = fminf(fminf(a2, __uint_as_float(vr[i + 2])), __uint_as_float(vr[i + 6]));
+                        a3 = fminf(fminf(a3, __uint_as_float(vr[i + 3])), __uint_as_float(vr[i + 7]));
+                    }
+#pragma unroll
+                    for (int i = 4 + ((SL - 4) / 8) * 8; i < SL; ++i)
+                        a0 = fminf(a0, __uint_as_float(vr[i]));
+                    const float ms = fminf(fminf(a0, a1), fminf(a2, a3));
+                    const float m_new = fminf(m_run, ms);
+                    // earlier candidates are out of range once the minimum drops by > delta
+                    // (the masks of this and the later slices are still zero)
+                    const bool drop = m_new + delta < m_run;
+#pragma unroll
+                    for (int a = 0; a < NS; ++a)
+#pragma unroll
+                        for (int w = 0; w < NW; ++w) mw[a][w] = drop ? 0u : mw[a][w];
+                    m_run = m_new;
+                    const float thr = m_run + delta;
+                    uint32_t cur[NW];
+#pragma unroll
+                    for (int w = 0; w < NW; ++w) cur[w] = 0u;
+                    if (sl == 0 || __any_sync(0xffffffffu, ms < thr)) {
+                        const uint64_t thr2 = pack2(thr, thr);
+#pragma unroll
+                        for (int i = 0; i < SL; i += 2) {
+                            uint32_t d0, d1;
+                            unpack2u(sub2(pack2u(vr[i], vr[i + 1]), thr2), d0, d1);  // FADD2
+                            cur[i >> 5] = __funnelshift_l(d0, cur[i >> 5], 1);
+                            cur[(i + 1) >> 5] = __funnelshift_l(d1, cur[(i + 1) >> 5], 1);
+                        }
+                    }
+#pragma unroll
+                    for (int a = 0; a < NS; ++a)
+#pragma unroll
+                        for (int w = 0; w < NW; ++w) mw[a][w] = a == sl ? cur[w] : mw[a][w];
+                }
+            } else {
 #pragma unroll
             for (int c = 0; c < NCH; ++c) {
                 uint32_t buf, bph;
@@ -1199,6 +1270,8 @@ bmu_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ T
                         }
                     }
                 }
+            }
+
             }
 
             if constexpr (NCH == 2 && !ACC) {
