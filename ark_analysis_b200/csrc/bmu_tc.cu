@@ -25,6 +25,13 @@
 //   warp 4*NG+1       : TMEM allocator + MMA issuer (one elected lane)
 // NG = 4 with 56-column slices (<= 112 registers/thread) for K <= 128, NG = 2 with wider slices
 // above that.  The epilogue is instruction-latency bound, so warps per scheduler matter.
+//
+// Two relatives of this kernel, both planned here:
+//   * bmu_x3_kernel.cuh -- assignment for K <= 104, C <= 24 with SPLIT tf32 operands (three MMAs per
+//     K-step): the candidate window is ~100x narrower and the recheck all but disappears;
+//   * the "tail8" layout (TcPlan::tail8, a template parameter of bmu_tc_kernel) -- for C8 % 32 == 8
+//     the last eight channels of the X tile and of the image are 32-byte SWIZZLE_32B rows instead
+//     of a 128-byte block that is three quarters zero fill (cfg3: 2 -> 6 pipeline stages).
 #include <float.h>
 #include <stdio.h>
 #include <stdlib.h>
